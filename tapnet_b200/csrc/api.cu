@@ -1,0 +1,118 @@
+// extern "C" surface of libtapir_b200.so (include/tapir_b200.h).
+#include "kernels.cuh"
+
+namespace tapir {
+const char* last_error();
+}
+
+using namespace tapir;
+
+namespace {
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+}  // namespace
+
+extern "C" {
+
+const char* tapir_last_error(void) { return tapir::last_error(); }
+int tapir_abi_version(void) { return TAPIR_B200_ABI_VERSION; }
+unsigned long long tapir_launch_count(void) { return tapir::g_launch_count; }
+
+int tapir_split_planes(const float* src, int64_t ld_src, void* dst, int64_t ld_dst,
+                       int64_t plane_stride, int64_t rows, int32_t cols, int32_t cols_padded,
+                       int32_t planes, void* stream) {
+  TAPIR_CHECK_ARG(src != nullptr && dst != nullptr, "tapir_split_planes: null pointer");
+  return split_planes(src, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst, plane_stride, rows, cols,
+                      cols_padded, planes, S(stream));
+}
+
+int tapir_gemm(const void* a_planes, int32_t lda, int64_t a_plane_stride, const tapir_linear* b,
+               int64_t M, int32_t conv3x3, int32_t frames, int32_t H, int32_t W, int32_t C,
+               const float* residual, int32_t ldr, int32_t act_gelu, float* out_f32, int32_t ldo,
+               void* out_planes, int32_t ldp, int64_t out_plane_stride, int32_t out_P,
+               int32_t impl, void* stream) {
+  TAPIR_CHECK_ARG(a_planes != nullptr && b != nullptr && b->w != nullptr, "tapir_gemm: null pointer");
+  TAPIR_CHECK_ARG(M > 0 && M < (1ll << 31), "tapir_gemm: M out of range");
+  GemmArgs g;
+  g.mode = conv3x3 ? kGemmConv3x3 : kGemmPlain;
+  g.planes = b->planes;
+  g.M = (int)M;
+  g.N = b->N;
+  g.K = b->K;
+  g.a = static_cast<const __nv_bfloat16*>(a_planes);
+  g.lda = lda;
+  g.a_plane_stride = a_plane_stride;
+  g.frames = frames; g.H = H; g.W = W; g.C = C;
+  g.b = static_cast<const __nv_bfloat16*>(b->w);
+  g.ldb = b->K;
+  g.b_plane_stride = (long long)b->N * b->K;
+  g.bias = b->bias;
+  g.residual = residual; g.ldr = ldr;
+  g.act = act_gelu ? 1 : 0;
+  g.out_f32 = out_f32; g.ldo = ldo;
+  g.out_planes = static_cast<__nv_bfloat16*>(out_planes);
+  g.ldp = ldp; g.out_plane_stride = out_plane_stride; g.out_P = out_P;
+  if (impl == 1) return gemm_simt(g, S(stream));
+  if (impl == 0) return gemm_tc(g, S(stream));
+  set_error("tapir_gemm: impl must be 0 (tcgen05) or 1 (simt)");
+  return kBadArgument;
+}
+
+int tapir_bilinear_resize(const float* src, int32_t frames, int32_t H, int32_t W, int32_t C,
+                          float* dst, int32_t oH, int32_t oW, void* stream) {
+  TAPIR_CHECK_ARG(src && dst && frames > 0 && H > 0 && W > 0 && C > 0 && oH > 0 && oW > 0,
+                  "tapir_bilinear_resize: bad arguments");
+  return bilinear_resize(src, frames, H, W, C, dst, oH, oW, S(stream));
+}
+
+size_t tapir_backbone_workspace_bytes(int32_t frames, int32_t H, int32_t W, int32_t extra_convs,
+                                      int32_t planes) {
+  return backbone_workspace_bytes(frames, H, W, extra_convs, planes);
+}
+
+int tapir_backbone_forward(const tapir_backbone_weights* w, const float* video, int32_t frames,
+                           int32_t H, int32_t W, float* lowres, float* hires, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return backbone_forward(w, video, frames, H, W, lowres, hires, workspace, workspace_bytes, S(stream));
+}
+
+int tapir_sample_query_features(const float* grid, int32_t T, int32_t gh, int32_t gw, int32_t C,
+                                const float* query_tyx, int32_t N, int32_t vT, int32_t vH,
+                                int32_t vW, float* out, void* stream) {
+  return sample_query_features(grid, T, gh, gw, C, query_tyx, N, vT, vH, vW, out, S(stream));
+}
+
+size_t tapir_cost_volume_workspace_bytes(int32_t N, int32_t T, int32_t gh, int32_t gw, int32_t C) {
+  return cost_volume_workspace_bytes(N, T, gh, gw, C);
+}
+
+int tapir_cost_volume_tracks(const tapir_head_weights* w, const float* qfeat, const float* grid,
+                             int32_t N, int32_t T, int32_t gh, int32_t gw, int32_t C,
+                             const float* query_tyx, float softmax_temperature, int32_t init_h,
+                             int32_t init_w, float* points, float* occ, float* expd,
+                             int32_t* argmax, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  return cost_volume_tracks(w, qfeat, grid, N, T, gh, gw, C, query_tyx, softmax_temperature, init_h,
+                            init_w, points, occ, expd, argmax, workspace, workspace_bytes, S(stream));
+}
+
+int tapir_pool_pyramid(const float* grid, int32_t T, int32_t h, int32_t w, int32_t C, float* out,
+                       void* stream) {
+  return pool_pyramid(grid, T, h, w, C, out, S(stream));
+}
+
+int tapir_local_corr(const tapir_corr_args* args, void* stream) { return local_corr(args, S(stream)); }
+
+size_t tapir_mixer_workspace_bytes(int64_t rows, int32_t planes) {
+  return mixer_workspace_bytes(rows, planes);
+}
+
+int tapir_mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return mixer_forward(w, io, workspace, workspace_bytes, S(stream));
+}
+
+int tapir_refine_update(const tapir_update_args* args, void* stream) {
+  return refine_update(args, S(stream));
+}
+
+}  // extern "C"

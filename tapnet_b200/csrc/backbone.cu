@@ -1,0 +1,606 @@
+// Feature-pyramid backbone: ResNet-V2 + InstanceNorm, ExtraConvs, L2 norm.
+// All 3x3 / 1x1 convolutions run as split-bf16 tcgen05 GEMMs (gemm_tc.cu); this file holds the
+// HBM-bound kernels around them (stem conv, instance/layer norm, im2col for the three
+// stride-2 layers, resize) and the per-frame-chunk orchestration.
+#include "kernels.cuh"
+
+namespace tapir {
+
+namespace {
+
+// ------------------------------------------------------------------------ split planes
+__global__ void split_planes_kernel(const float* __restrict__ src, long long ld_src,
+                                    __nv_bfloat16* __restrict__ dst, long long ld_dst,
+                                    long long plane_stride, long long rows, int cols,
+                                    int cols_padded, int planes) {
+  const long long total = rows * cols_padded;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_padded;
+    const int c = (int)(i - r * cols_padded);
+    float v = (c < cols) ? src[r * ld_src + c] : 0.f;
+    for (int q = 0; q < planes; ++q) {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      v -= __bfloat162float(h);
+      dst[q * plane_stride + r * ld_dst + c] = h;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ stem conv
+// nets.py:395-402,420: F.pad(x,(2,4,2,4)) then 7x7 stride-2 conv, 3 -> 64, no bias.
+// CTA = 16x16 output pixels; each thread owns one pixel and all 64 output channels.
+constexpr int kStemTile = 16;
+constexpr int kStemPatch = 2 * kStemTile + 5;  // 37 input pixels per side
+
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ video,
+                                                        const float* __restrict__ w, int H, int W,
+                                                        float* __restrict__ out) {
+  extern __shared__ float stem_smem[];
+  float* ws = stem_smem;                    // [147][64]
+  float* patch = stem_smem + 147 * 64;      // [37][37][3]
+  const int OH = H / 2, OW = W / 2;
+  const int f = blockIdx.z;
+  const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
+  for (int i = threadIdx.x; i < 147 * 64; i += 256) ws[i] = w[i];
+  const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
+  for (int i = threadIdx.x; i < kStemPatch * kStemPatch * 3; i += 256) {
+    const int c = i % 3, px = (i / 3) % kStemPatch, py = i / (3 * kStemPatch);
+    const int y = iy0 + py, x = ix0 + px;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) v = video[(((long long)f * H + y) * W + x) * 3 + c];
+    patch[i] = v;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / kStemTile, tx = threadIdx.x % kStemTile;
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  for (int ky = 0; ky < 7; ++ky) {
+    for (int kx = 0; kx < 7; ++kx) {
+      const float* pp = patch + ((2 * ty + ky) * kStemPatch + (2 * tx + kx)) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = pp[c];
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 7 + kx) * 3 + c) * 64);
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          const float4 w4 = wr[o];
+          acc[4 * o + 0] = fmaf(v, w4.x, acc[4 * o + 0]);
+          acc[4 * o + 1] = fmaf(v, w4.y, acc[4 * o + 1]);
+          acc[4 * o + 2] = fmaf(v, w4.z, acc[4 * o + 2]);
+          acc[4 * o + 3] = fmaf(v, w4.w, acc[4 * o + 3]);
+        }
+      }
+    }
+  }
+  if (oy < OH && ox < OW) {
+    float4* o = reinterpret_cast<float4*>(out + (((long long)f * OH + oy) * OW + ox) * 64);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  }
+}
+
+// ------------------------------------------------------------------------ instance norm
+// nets.py:280-286: per (frame, channel) statistics over H*W, biased variance, eps 1e-5.
+// Sums are accumulated in fp64 (sum, sum of squares) so E[x^2]-E[x]^2 is exact to fp32.
+constexpr int kStatPixelsPerBlock = 1024;
+
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __restrict__ x,
+                                                             long long hw, int C,
+                                                             double* __restrict__ sums) {
+  __shared__ double red[256 * 8];
+  const int f = blockIdx.y;
+  const int c4n = C / 4;             // float4 groups per pixel
+  const int lanes = 256 / c4n;       // pixel lanes per block
+  const int g = threadIdx.x % c4n, pl = threadIdx.x / c4n;
+  const long long p0 = (long long)blockIdx.x * kStatPixelsPerBlock;
+  long long p1 = p0 + kStatPixelsPerBlock;
+  if (p1 > hw) p1 = hw;
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  if (pl < lanes) {
+    const float4* base = reinterpret_cast<const float4*>(x + (long long)f * hw * C);
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      const float4 v = base[p * c4n + g];
+      s[0] += v.x; ss[0] += (double)v.x * v.x;
+      s[1] += v.y; ss[1] += (double)v.y * v.y;
+      s[2] += v.z; ss[2] += (double)v.z * v.z;
+      s[3] += v.w; ss[3] += (double)v.w * v.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[threadIdx.x * 8 + i] = s[i];
+    red[threadIdx.x * 8 + 4 + i] = ss[i];
+  }
+  __syncthreads();
+  // thread t < C reduces channel t over the pixel lanes
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    const int gg = c / 4, e = c % 4;
+    double a = 0, b = 0;
+    for (int l = 0; l < lanes; ++l) {
+      a += red[(l * c4n + gg) * 8 + e];
+      b += red[(l * c4n + gg) * 8 + 4 + e];
+    }
+    atomicAdd(&sums[((long long)f * C + c) * 2 + 0], a);
+    atomicAdd(&sums[((long long)f * C + c) * 2 + 1], b);
+  }
+}
+
+__global__ void __launch_bounds__(256) instnorm_finalize_kernel(const double* __restrict__ sums,
+                                                                long long hw, int count,
+                                                                float* __restrict__ mr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double mean = sums[2 * i] / (double)hw;
+  double var = sums[2 * i + 1] / (double)hw - mean * mean;
+  if (var < 0) var = 0;
+  mr[2 * i] = (float)mean;
+  mr[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+}
+
+__global__ void __launch_bounds__(256) instnorm_relu_split_kernel(
+    const float* __restrict__ x, const float* __restrict__ mr, const float* __restrict__ w,
+    const float* __restrict__ b, long long hw, int C, __nv_bfloat16* __restrict__ out,
+    long long plane_stride, int planes, long long total4) {
+  const int c4n = C / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % c4n);
+    const long long pix = i / c4n;
+    const long long f = pix / hw;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float in[4] = {v.x, v.y, v.z, v.w};
+    float y[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = g * 4 + e;
+      const float2 st = reinterpret_cast<const float2*>(mr)[f * C + c];
+      const float t = (in[e] - st.x) * st.y * w[c] + b[c];
+      y[e] = fmaxf(t, 0.f);
+    }
+    for (int q = 0; q < planes; ++q) {
+      __nv_bfloat16 h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h[e] = __float2bfloat16_rn(y[e]);
+        y[e] -= __bfloat162float(h[e]);
+      }
+      uint2 pk;
+      pk.x = pack_bf16x2(h[0], h[1]);
+      pk.y = pack_bf16x2(h[2], h[3]);
+      reinterpret_cast<uint2*>(out + q * plane_stride)[i] = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ im2col, stride 2
+// nets.py:258-267,320: stride-2 3x3 convs see F.pad(x,(0,2,0,2)): tap (ky,kx) reads
+// in[2y+ky, 2x+kx], zero beyond the border; the 1x1 stride-2 projection reads in[2y,2x].
+__global__ void __launch_bounds__(256) im2col_s2_kernel(const __nv_bfloat16* __restrict__ in,
+                                                        long long in_plane_stride, int H, int W,
+                                                        int C, int taps,
+                                                        __nv_bfloat16* __restrict__ out,
+                                                        long long out_plane_stride, int planes,
+                                                        long long total8) {
+  const int OH = H / 2, OW = W / 2;
+  const int c8n = C / 8;
+  const int kside = (taps == 9) ? 3 : 1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % c8n);
+    long long r = i / c8n;
+    const int tap = (int)(r % taps);
+    r /= taps;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const long long f = r / OH;
+    const int y = 2 * oy + tap / kside, x = 2 * ox + tap % kside;
+    const bool ok = (y < H) && (x < W);
+    const long long src = (((f * H + y) * W + x) * C) / 8 + g;
+    for (int q = 0; q < planes; ++q) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ok) v = reinterpret_cast<const uint4*>(in + q * in_plane_stride)[src];
+      reinterpret_cast<uint4*>(out + q * out_plane_stride)[i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ layer norm
+// nets.py:37-39,56 (affine+bias, channel-last) and nets.py:118-120,138-140 (scale only).
+// One warp per row; C in {256, 512}.
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_split_kernel(
+    const float* __restrict__ x, long long rows, const float* __restrict__ w,
+    const float* __restrict__ b, float* __restrict__ y, __nv_bfloat16* __restrict__ pl,
+    long long plane_stride, int planes) {
+  constexpr int V = C / 128;  // float4 per lane
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += a * a + bb * bb + c * c + d * d;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) * (1.0f / C) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    const float4 ww = reinterpret_cast<const float4*>(w)[i * 32 + lane];
+    float o[4] = {(v[i].x - mean) * rstd * ww.x, (v[i].y - mean) * rstd * ww.y,
+                  (v[i].z - mean) * rstd * ww.z, (v[i].w - mean) * rstd * ww.w};
+    if (b != nullptr) {
+      const float4 bb = reinterpret_cast<const float4*>(b)[i * 32 + lane];
+      o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+    }
+    if (y != nullptr) *reinterpret_cast<float4*>(y + row * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
+    if (pl != nullptr) {
+      for (int q = 0; q < planes; ++q) {
+        __nv_bfloat16 h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h[e] = __float2bfloat16_rn(o[e]);
+          o[e] -= __bfloat162float(h[e]);
+        }
+        uint2 pk;
+        pk.x = pack_bf16x2(h[0], h[1]);
+        pk.y = pack_bf16x2(h[2], h[3]);
+        *reinterpret_cast<uint2*>(pl + q * plane_stride + row * C + c0) = pk;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ L2 normalise
+// tapir_model.py:370-381: x / sqrt(max(sum x^2, 1e-12)) over channels.
+template <int C>
+__global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, long long rows,
+                                                     float* __restrict__ out) {
+  constexpr int V = C / 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float d = sqrtf(fmaxf(warp_sum(s), 1e-12f));
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+    reinterpret_cast<float4*>(out + row * C)[i * 32 + lane] =
+        make_float4(v[i].x / d, v[i].y / d, v[i].z / d, v[i].w / d);
+}
+
+// ------------------------------------------------------------------------ bilinear resize
+// utils.py:26-42 -> F.interpolate(mode='bilinear', align_corners=False), no antialias.
+__global__ void __launch_bounds__(256) bilinear_resize_kernel(const float* __restrict__ src, int H,
+                                                              int W, int C, float* __restrict__ dst,
+                                                              int oH, int oW, long long total) {
+  const float sy = (float)H / (float)oH, sx = (float)W / (float)oW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int ox = (int)(r % oW);
+    r /= oW;
+    const int oy = (int)(r % oH);
+    const long long f = r / oH;
+    float fy = sy * (oy + 0.5f) - 0.5f;
+    float fx = sx * (ox + 0.5f) - 0.5f;
+    if (fy < 0.f) fy = 0.f;
+    if (fx < 0.f) fx = 0.f;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + ((y0 < H - 1) ? 1 : 0), x1 = x0 + ((x0 < W - 1) ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* b = src + f * (long long)H * W * C;
+    const float v00 = b[((long long)y0 * W + x0) * C + c], v01 = b[((long long)y0 * W + x1) * C + c];
+    const float v10 = b[((long long)y1 * W + x0) * C + c], v11 = b[((long long)y1 * W + x1) * C + c];
+    dst[i] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+  }
+}
+
+int grid_for(long long total, int block = 256) {
+  long long g = ceil_div_ll(total, block);
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+int split_planes(const float* src, long long ld_src, __nv_bfloat16* dst, long long ld_dst,
+                 long long plane_stride, long long rows, int cols, int cols_padded, int planes,
+                 cudaStream_t s) {
+  TAPIR_CHECK_ARG(planes >= 1 && planes <= 3 && rows > 0 && cols > 0 && cols_padded >= cols &&
+                      ld_dst >= cols_padded && ld_src >= cols,
+                  "split_planes: bad shape rows=%lld cols=%d padded=%d", rows, cols, cols_padded);
+  const long long total = rows * cols_padded;
+  split_planes_kernel<<<grid_for(total), 256, 0, s>>>(src, ld_src, dst, ld_dst, plane_stride, rows,
+                                                     cols, cols_padded, planes);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("split_planes_kernel");
+  return kOk;
+}
+
+int stem_conv(const float* video, const float* w_packed, int frames, int H, int W, float* out,
+              cudaStream_t s) {
+  TAPIR_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "stem_conv: H, W must be even");
+  const int smem = (147 * 64 + kStemPatch * kStemPatch * 3) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    TAPIR_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(W / 2, kStemTile), ceil_div(H / 2, kStemTile), frames);
+  stem_conv_kernel<<<grid, 256, smem, s>>>(video, w_packed, H, W, out);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("stem_conv_kernel");
+  return kOk;
+}
+
+int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, float* mr,
+                   cudaStream_t s) {
+  TAPIR_CHECK_ARG(C == 64 || C == 128 || C == 256, "instnorm_stats: C=%d unsupported", C);
+  TAPIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * frames * C, s));
+  dim3 grid((unsigned)ceil_div_ll(hw, kStatPixelsPerBlock), frames);
+  instnorm_stats_kernel<<<grid, 256, 0, s>>>(x, hw, C, sums);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("instnorm_stats_kernel");
+  instnorm_finalize_kernel<<<ceil_div(frames * C, 256), 256, 0, s>>>(sums, hw, frames * C, mr);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("instnorm_finalize_kernel");
+  return kOk;
+}
+
+int instnorm_relu_split(const float* x, const float* mr, const float* w, const float* b,
+                        int frames, long long hw, int C, __nv_bfloat16* out, long long plane_stride,
+                        int planes, cudaStream_t s) {
+  const long long total4 = (long long)frames * hw * C / 4;
+  instnorm_relu_split_kernel<<<grid_for(total4), 256, 0, s>>>(x, mr, w, b, hw, C, out,
+                                                             plane_stride, planes, total4);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("instnorm_relu_split_kernel");
+  return kOk;
+}
+
+int im2col_s2(const __nv_bfloat16* in, long long in_plane_stride, int frames, int H, int W, int C,
+              int taps, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t s) {
+  TAPIR_CHECK_ARG((taps == 1 || taps == 9) && C % 8 == 0 && H % 2 == 0 && W % 2 == 0,
+                  "im2col_s2: bad arguments");
+  const long long total8 = (long long)frames * (H / 2) * (W / 2) * taps * (C / 8);
+  im2col_s2_kernel<<<grid_for(total8), 256, 0, s>>>(in, in_plane_stride, H, W, C, taps, out,
+                                                   out_plane_stride, planes, total8);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("im2col_s2_kernel");
+  return kOk;
+}
+
+int layernorm_split(const float* x, long long rows, int C, const float* w, const float* b,
+                    float* y, __nv_bfloat16* planes_out, long long plane_stride, int planes,
+                    cudaStream_t s) {
+  const unsigned grid = (unsigned)ceil_div_ll(rows, 8);
+  if (C == 256) {
+    layernorm_split_kernel<256><<<grid, 256, 0, s>>>(x, rows, w, b, y, planes_out, plane_stride, planes);
+  } else if (C == 512) {
+    layernorm_split_kernel<512><<<grid, 256, 0, s>>>(x, rows, w, b, y, planes_out, plane_stride, planes);
+  } else {
+    set_error("layernorm_split: C=%d unsupported", C);
+    return kUnsupported;
+  }
+  count_launch();
+  TAPIR_LAUNCH_CHECK("layernorm_split_kernel");
+  return kOk;
+}
+
+int l2_normalize(const float* x, long long rows, int C, float* out, cudaStream_t s) {
+  const unsigned grid = (unsigned)ceil_div_ll(rows, 8);
+  if (C == 128) {
+    l2norm_kernel<128><<<grid, 256, 0, s>>>(x, rows, out);
+  } else if (C == 256) {
+    l2norm_kernel<256><<<grid, 256, 0, s>>>(x, rows, out);
+  } else {
+    set_error("l2_normalize: C=%d unsupported", C);
+    return kUnsupported;
+  }
+  count_launch();
+  TAPIR_LAUNCH_CHECK("l2norm_kernel");
+  return kOk;
+}
+
+int bilinear_resize(const float* src, int frames, int H, int W, int C, float* dst, int oH, int oW,
+                    cudaStream_t s) {
+  const long long total = (long long)frames * oH * oW * C;
+  bilinear_resize_kernel<<<grid_for(total), 256, 0, s>>>(src, H, W, C, dst, oH, oW, total);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("bilinear_resize_kernel");
+  return kOk;
+}
+
+// ------------------------------------------------------------------------ orchestration
+
+namespace {
+
+struct BackbonePlan {
+  float* buf[4];            // fp32 activation buffers (ping-pong / shortcut / conv_0 output)
+  __nv_bfloat16* act;       // normalised activation planes
+  __nv_bfloat16* col;       // im2col planes (stride-2 layers) / ExtraConvs hidden planes
+  double* sums;             // instance-norm statistics (fp64 sum, sum of squares)
+  float* mr;                // finalised (mean, rstd) per (frame, channel)
+  long long act_plane, col_plane;
+};
+
+size_t plan_backbone(Arena& a, int frames, int H, int W, int extra, int planes, BackbonePlan* bp) {
+  const long long px = (long long)frames * H * W;
+  const long long act_elems = px / 4 * 64;  // largest activation: [F, H/2, W/2, 64] == 16*px
+  for (int i = 0; i < 4; ++i) bp->buf[i] = a.take<float>(act_elems);
+  bp->act_plane = act_elems;
+  bp->act = a.take<__nv_bfloat16>(act_elems * planes);
+  // im2col of group-1 conv_0: [F*H/4*W/4, 9*64]; ExtraConvs hidden: [F*H/8*W/8, 1024]
+  long long col_elems = px / 16 * 576;
+  const long long hid = px / 64 * 1024;
+  if (extra && hid > col_elems) col_elems = hid;
+  bp->col_plane = col_elems;
+  bp->col = a.take<__nv_bfloat16>(col_elems * planes);
+  bp->sums = a.take<double>((size_t)frames * 256 * 2);
+  bp->mr = a.take<float>((size_t)frames * 256 * 2);
+  return a.off;
+}
+
+GemmArgs linear_args(const tapir_linear& l) {
+  GemmArgs g;
+  g.planes = l.planes;
+  g.N = l.N;
+  g.K = l.K;
+  g.b = static_cast<const __nv_bfloat16*>(l.w);
+  g.ldb = l.K;
+  g.b_plane_stride = (long long)l.N * l.K;
+  g.bias = l.bias;
+  return g;
+}
+
+}  // namespace
+
+size_t backbone_workspace_bytes(int frames, int H, int W, int extra_convs, int planes) {
+  Arena a(nullptr, 0);
+  BackbonePlan bp;
+  return plan_backbone(a, frames, H, W, extra_convs, planes, &bp) + 256;
+}
+
+int backbone_forward(const tapir_backbone_weights* w, const float* video, int frames, int H, int W,
+                     float* lowres, float* hires, void* ws, size_t ws_bytes, cudaStream_t s) {
+  TAPIR_CHECK_ARG(w != nullptr && video != nullptr && lowres != nullptr && hires != nullptr,
+                  "backbone_forward: null pointer");
+  TAPIR_CHECK_ARG(frames > 0 && H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16,
+                  "backbone_forward: image resolution must be a multiple of 8 (H=%d W=%d)", H, W);
+  const int P = w->planes;
+  TAPIR_CHECK_ARG(P >= 1 && P <= 3, "backbone_forward: planes=%d", P);
+  Arena arena(ws, ws_bytes);
+  BackbonePlan bp;
+  plan_backbone(arena, frames, H, W, w->num_extra > 0, P, &bp);
+  if (!arena.ok) {
+    set_error("backbone_forward: workspace too small (%zu < %zu)", ws_bytes, arena.off);
+    return kWorkspaceTooSmall;
+  }
+
+  int h = H / 2, wd = W / 2;
+  float* x = bp.buf[0];
+  TAPIR_RETURN_IF(stem_conv(video, w->stem_w, frames, H, W, x, s));
+  int xi = 0;  // index of the buffer holding x
+  for (int bi = 0; bi < TAPIR_NUM_RESNET_BLOCKS; ++bi) {
+    const tapir_resnet_block& b = w->blocks[bi];
+    const long long m_in = (long long)frames * h * wd;
+    const int oh = h / b.stride, ow = wd / b.stride;
+    const long long m_out = (long long)frames * oh * ow;
+    float* xnew = bp.buf[(xi + 1) & 3];
+    float* shortcut_buf = bp.buf[(xi + 2) & 3];
+    float* hbuf = bp.buf[(xi + 3) & 3];
+    // bn_0 + relu -> planes
+    TAPIR_RETURN_IF(instnorm_stats(x, frames, (long long)h * wd, b.cin, bp.sums, bp.mr, s));
+    TAPIR_RETURN_IF(instnorm_relu_split(x, bp.mr, b.bn0_w, b.bn0_b, frames, (long long)h * wd,
+                                        b.cin, bp.act, bp.act_plane, P, s));
+    const float* shortcut = x;
+    if (b.has_proj) {
+      GemmArgs g = linear_args(b.proj);
+      g.M = (int)m_out;
+      g.out_f32 = shortcut_buf;
+      g.ldo = b.cout;
+      if (b.stride == 1) {
+        g.a = bp.act; g.lda = b.cin; g.a_plane_stride = bp.act_plane;
+      } else {
+        TAPIR_RETURN_IF(im2col_s2(bp.act, bp.act_plane, frames, h, wd, b.cin, 1, bp.col, bp.col_plane, P, s));
+        g.a = bp.col; g.lda = b.cin; g.a_plane_stride = bp.col_plane;
+      }
+      TAPIR_RETURN_IF(gemm(g, s));
+      shortcut = shortcut_buf;
+    }
+    {
+      GemmArgs g = linear_args(b.conv0);
+      g.M = (int)m_out;
+      g.out_f32 = hbuf;
+      g.ldo = b.cout;
+      if (b.stride == 1) {
+        g.mode = kGemmConv3x3;
+        g.a = bp.act; g.a_plane_stride = bp.act_plane;
+        g.frames = frames; g.H = h; g.W = wd; g.C = b.cin;
+      } else {
+        TAPIR_RETURN_IF(im2col_s2(bp.act, bp.act_plane, frames, h, wd, b.cin, 9, bp.col, bp.col_plane, P, s));
+        g.a = bp.col; g.lda = 9 * b.cin; g.a_plane_stride = bp.col_plane;
+      }
+      TAPIR_RETURN_IF(gemm(g, s));
+    }
+    TAPIR_RETURN_IF(instnorm_stats(hbuf, frames, (long long)oh * ow, b.cout, bp.sums, bp.mr, s));
+    TAPIR_RETURN_IF(instnorm_relu_split(hbuf, bp.mr, b.bn1_w, b.bn1_b, frames, (long long)oh * ow,
+                                        b.cout, bp.act, bp.act_plane, P, s));
+    {
+      GemmArgs g = linear_args(b.conv1);
+      g.mode = kGemmConv3x3;
+      g.M = (int)m_out;
+      g.a = bp.act; g.a_plane_stride = bp.act_plane;
+      g.frames = frames; g.H = oh; g.W = ow; g.C = b.cout;
+      g.residual = shortcut; g.ldr = b.cout;
+      g.out_f32 = xnew; g.ldo = b.cout;
+      TAPIR_RETURN_IF(gemm(g, s));
+    }
+    x = xnew;
+    xi = (xi + 1) & 3;
+    h = oh;
+    wd = ow;
+    (void)m_in;
+    if (bi == 3) {  // resnet_unit_1 -> hires (tapir_model.py:356,376-381)
+      TAPIR_RETURN_IF(l2_normalize(x, m_out, b.cout, hires, s));
+    }
+  }
+  const long long m = (long long)frames * h * wd;
+  for (int e = 0; e < w->num_extra; ++e) {
+    const tapir_extra_block& b = w->extra[e];
+    float* y = bp.buf[(xi + 1) & 3];
+    float* xnew = bp.buf[(xi + 2) & 3];
+    TAPIR_RETURN_IF(layernorm_split(x, m, 256, b.ln_w, b.ln_b, y, bp.act, bp.act_plane, P, s));
+    {
+      GemmArgs g = linear_args(b.conv);
+      g.mode = kGemmConv3x3;
+      g.M = (int)m;
+      g.a = bp.act; g.a_plane_stride = bp.act_plane;
+      g.frames = frames; g.H = h; g.W = wd; g.C = 256;
+      g.act = 1;
+      g.out_planes = bp.col; g.ldp = b.conv.N; g.out_plane_stride = bp.col_plane; g.out_P = P;
+      TAPIR_RETURN_IF(gemm(g, s));
+    }
+    {
+      GemmArgs g = linear_args(b.conv1);
+      g.mode = kGemmConv3x3;
+      g.M = (int)m;
+      g.a = bp.col; g.a_plane_stride = bp.col_plane;
+      g.frames = frames; g.H = h; g.W = wd; g.C = b.conv.N;
+      g.residual = y; g.ldr = 256;
+      g.out_f32 = xnew; g.ldo = 256;
+      TAPIR_RETURN_IF(gemm(g, s));
+    }
+    x = xnew;
+    xi = (xi + 2) & 3;
+  }
+  TAPIR_RETURN_IF(l2_normalize(x, m, 256, lowres, s));
+  return kOk;
+}
+
+}  // namespace tapir

@@ -1,0 +1,106 @@
+// Shared device/host helpers for the tapir_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+
+namespace tapir {
+
+// ---------------------------------------------------------------------------------------
+// error plumbing: every extern "C" entry returns 0 on success; message via tapir_last_error
+// ---------------------------------------------------------------------------------------
+enum Status : int {
+  kOk = 0,
+  kBadArgument = 1,
+  kUnsupported = 2,
+  kCudaError = 3,
+  kWorkspaceTooSmall = 4,
+};
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define TAPIR_CHECK_ARG(cond, ...)                 \
+  do {                                             \
+    if (!(cond)) {                                 \
+      ::tapir::set_error(__VA_ARGS__);             \
+      return ::tapir::kBadArgument;                \
+    }                                              \
+  } while (0)
+
+#define TAPIR_CUDA(expr)                                        \
+  do {                                                          \
+    cudaError_t _e = (expr);                                    \
+    if (_e != cudaSuccess) return ::tapir::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define TAPIR_LAUNCH_CHECK(name)                                     \
+  do {                                                               \
+    cudaError_t _e = cudaGetLastError();                             \
+    if (_e != cudaSuccess) return ::tapir::cuda_fail(_e, name);      \
+  } while (0)
+
+#define TAPIR_RETURN_IF(expr)        \
+  do {                               \
+    int _s = (expr);                 \
+    if (_s != 0) return _s;          \
+  } while (0)
+
+int num_sms();
+
+// counts kernels launched by this library (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// tanh-approximated GELU, F.gelu(x, approximate='tanh') (nets.py:59,102,160):
+//   0.5 x (1 + tanh(k (x + 0.044715 x^3))) == x * sigmoid(2 k (x + 0.044715 x^3))
+// evaluated through ex2.approx (|rel err| ~1e-6, far inside the 1e-4 logit budget).
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k2 = 1.5957691216057308f;  // 2*sqrt(2/pi)
+  float u = k2 * (x + 0.044715f * x * x * x);
+  float e = __expf(-u);
+  return __fdividef(x, 1.0f + e);
+}
+
+// Split an fp32 value into P bf16 terms: x ~= p0 + p1 (+ p2); each term is the bf16
+// rounding of the remaining residual.  P=2 carries ~16 mantissa bits, P=3 all 24.
+template <int P>
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 (&out)[P]) {
+  float r = x;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    out[i] = __float2bfloat16_rn(r);
+    r = r - __bfloat162float(out[i]);
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace tapir

@@ -1,0 +1,504 @@
+// tcgen05 / TMEM / TMA split-bf16 GEMM and implicit-GEMM 3x3 convolution for sm_100a.
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor tiles of A and B planes into a
+//                      multi-stage shared-memory ring (128B-swizzled, K-major)
+//   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16,
+//                      fp32 accumulators in TMEM (double buffered: 2 x BLOCK_N columns)
+//   warps 2..5         epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row
+//                      per thread), bias / tanh-GELU / residual, store fp32 and/or bf16 planes
+// Pipelines: full/empty mbarriers between TMA and MMA, tmem_full/tmem_empty between MMA and
+// epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// A operand, plain mode: 3-D tensor map {K, M, plane}, box {64, 128, 1}.
+// A operand, conv mode : 5-D tensor map {C, W, H, frame, plane} over the NHWC activation,
+//   box {64, tileW, tileH, 1, 1}; the 3x3 taps are shifted box origins, and TMA's
+//   out-of-bounds zero fill implements the zero padding (nets.py:296-303,40-53 padding=1).
+// B operand: 3-D tensor map {K, N, plane}, box {64, BLOCK_N, 1}.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace tapir {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kNumAccStages = 2;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kBarrierBytes = 256;
+
+struct TcParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int M, N;
+  int num_k_blocks;
+  int num_m_tiles, num_n_tiles;
+  int mode;
+  int H, W, cblocks, tileW, tileH, tiles_x, tiles_y;
+  const float* bias;
+  const float* residual;
+  int ldr;
+  int act;
+  float* out_f32;
+  int ldo;
+  __nv_bfloat16* out_planes;
+  int ldp;
+  long long out_plane_stride;
+  int out_P;
+  int* err;
+};
+
+template <int BLOCK_N, int P>
+struct TcCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = P * (kABytes + kBBytes);
+  static constexpr int kAvail = kSmemLimit - 1024 - kBarrierBytes;
+  static constexpr int kStagesRaw = kAvail / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarrierBytes;
+  static constexpr int kTmemCols = (kNumAccStages * BLOCK_N <= 128) ? 128
+                                   : (kNumAccStages * BLOCK_N <= 256) ? 256 : 512;
+  static_assert(kStages >= 1, "tile does not fit in shared memory");
+  static_assert(kStages * 2 + 2 * kNumAccStages <= (kBarrierBytes - 16) / 8, "barrier space");
+};
+
+__device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row, int col0,
+                                                const uint32_t (&acc)[32]) {
+  const bool full = (col0 + 32 <= p.N);
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  if (p.bias != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+    }
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+  }
+  if (p.residual != nullptr) {
+    const float* r = p.residual + row * (long long)p.ldr + col0;
+    if (full && (p.ldr & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = *reinterpret_cast<const float4*>(r + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] += r[j];
+    }
+  }
+  if (p.out_f32 != nullptr) {
+    float* o = p.out_f32 + row * (long long)p.ldo + col0;
+    if (full && (p.ldo & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) o[j] = v[j];
+    }
+  }
+  if (p.out_planes != nullptr) {
+    // successive bf16 terms of v: plane q holds bf16(v - sum_{r<q} plane r)
+    for (int q = 0; q < p.out_P; ++q) {
+      __nv_bfloat16* o = p.out_planes + q * p.out_plane_stride + row * (long long)p.ldp + col0;
+      if (full && (p.ldp & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          __nv_bfloat16 h[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            h[t] = __float2bfloat16_rn(v[j + t]);
+            v[j + t] -= __bfloat162float(h[t]);
+          }
+          uint4 w;
+          w.x = pack_bf16x2(h[0], h[1]);
+          w.y = pack_bf16x2(h[2], h[3]);
+          w.z = pack_bf16x2(h[4], h[5]);
+          w.w = pack_bf16x2(h[6], h[7]);
+          *reinterpret_cast<uint4*>(o + j) = w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+          v[j] -= __bfloat162float(h);
+          if (col0 + j < p.N) o[j] = h;
+        }
+      }
+    }
+  }
+}
+
+template <int BLOCK_N, int P>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<BLOCK_N, P>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + kNumAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kNumAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < kNumAccStages; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&p.tmA);
+    ptx::prefetch_tensormap(&p.tmB);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int nkb = p.num_k_blocks;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      int frame = 0, y0 = 0, x0 = 0;
+      if (p.mode == kGemmConv3x3) {
+        const int per_frame = p.tiles_x * p.tiles_y;
+        frame = m_tile / per_frame;
+        const int r = m_tile % per_frame;
+        y0 = (r / p.tiles_x) * p.tileH;
+        x0 = (r % p.tiles_x) * p.tileW;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 101);
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + P * Cfg::kABytes;
+        if (p.mode == kGemmConv3x3) {
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          const int ky = tap / 3, kx = tap - ky * 3;
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl)
+            ptx::tma_load_5d(sa + pl * Cfg::kABytes, &p.tmA, &full_bar[stage], cb * kBlockK,
+                             x0 + kx - 1, y0 + ky - 1, frame, pl);
+        } else {
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl)
+            ptx::tma_load_3d(sa + pl * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * kBlockK,
+                             m_tile * kBlockM, pl);
+        }
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl)
+          ptx::tma_load_3d(sb + pl * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, n0, pl);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, p.err, 102);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase, p.err, 103);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + P * Cfg::kABytes;
+        uint32_t accumulate = (kb > 0) ? 1u : 0u;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+#pragma unroll
+          for (int j = 0; j < P - i; ++j) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(sa + i * Cfg::kABytes);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + j * Cfg::kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
+              ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+              accumulate = 1u;
+            }
+          }
+        }
+        ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+      ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      const int r = q * 32 + lane;
+      long long row;
+      bool row_ok;
+      if (p.mode == kGemmConv3x3) {
+        const int per_frame = p.tiles_x * p.tiles_y;
+        const int frame = m_tile / per_frame;
+        const int rr = m_tile % per_frame;
+        const int y = (rr / p.tiles_x) * p.tileH + r / p.tileW;
+        const int x = (rr % p.tiles_x) * p.tileW + r % p.tileW;
+        row_ok = (y < p.H) && (x < p.W);
+        row = ((long long)frame * p.H + y) * p.W + x;
+      } else {
+        row = (long long)m_tile * kBlockM + r;
+        row_ok = row < p.M;
+      }
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 104);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
+        ptx::tmem_ld_wait();
+        if (row_ok) store_row_chunk(p, row, col0, v);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    return kCudaError;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (base=%p rank=%d dims=%llu,%llu,%llu "
+              "stride0=%llu box=%u,%u,%u)",
+              what, (int)r, base, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)dims[2], (unsigned long long)strides_bytes[0], box[0], box[1], box[2]);
+    return kCudaError;
+  }
+  return kOk;
+}
+
+int* device_error_flag() {
+  static int* flag = nullptr;
+  if (flag == nullptr) {
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+void choose_conv_tile(int H, int W, int* tw, int* th) {
+  long long best = -1;
+  for (int w = 128; w >= 8; w >>= 1) {
+    const int h = 128 / w;
+    const long long tiles = (long long)ceil_div(W, w) * ceil_div(H, h);
+    if (best < 0 || tiles < best) { best = tiles; *tw = w; *th = h; }
+  }
+}
+
+template <int BLOCK_N, int P>
+int launch(const TcParams& p, cudaStream_t stream) {
+  using Cfg = TcCfg<BLOCK_N, P>;
+  static bool configured = false;
+  if (!configured) {
+    TAPIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, P>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<BLOCK_N, P><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("gemm_tc_kernel");
+  return kOk;
+}
+
+int pick_block_n(int m_tiles, int N, int P) {
+  const char* force = getenv("TAPIR_B200_BLOCK_N");
+  if (force != nullptr) {
+    int v = atoi(force);
+    if (v == 64 || v == 128 || (v == 256 && P <= 2)) return v;
+  }
+  if (N <= 64) return 64;
+  if (P >= 3 || N <= 128) return 128;
+  // fewest (waves x tile width); 256-wide tiles re-read A half as often, so prefer on ties
+  const int sms = num_sms();
+  const long long c128 = (long long)ceil_div(m_tiles * ceil_div(N, 128), sms) * 128;
+  const long long c256 = (long long)ceil_div(m_tiles * ceil_div(N, 256), sms) * 256;
+  return (c256 <= c128) ? 256 : 128;
+}
+
+}  // namespace
+
+int validate_gemm_args(const GemmArgs& g) {
+  TAPIR_CHECK_ARG(g.planes >= 1 && g.planes <= 3, "gemm: planes must be 1..3 (got %d)", g.planes);
+  TAPIR_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  TAPIR_CHECK_ARG(g.K % kBlockK == 0, "gemm: K=%d must be a multiple of 64 (pad with zeros)", g.K);
+  TAPIR_CHECK_ARG(g.a != nullptr && g.b != nullptr, "gemm: null operand");
+  TAPIR_CHECK_ARG((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0,
+                  "gemm: operands must be 16-byte aligned");
+  TAPIR_CHECK_ARG(g.ldb >= g.K && g.ldb % 8 == 0, "gemm: ldb=%d must be >= K and a multiple of 8", g.ldb);
+  TAPIR_CHECK_ARG(g.b_plane_stride % 8 == 0 && g.a_plane_stride % 8 == 0, "gemm: plane strides must be multiples of 8 elements");
+  if (g.mode == kGemmConv3x3) {
+    TAPIR_CHECK_ARG(g.C % kBlockK == 0 && g.K == 9 * g.C, "gemm(conv): C=%d must be a multiple of 64 and K=9*C", g.C);
+    TAPIR_CHECK_ARG(g.frames > 0 && g.H > 0 && g.W > 0 && (long long)g.frames * g.H * g.W == g.M,
+                    "gemm(conv): M must equal frames*H*W");
+  } else {
+    TAPIR_CHECK_ARG(g.mode == kGemmPlain, "gemm: unknown mode %d", g.mode);
+    TAPIR_CHECK_ARG(g.lda >= g.K && g.lda % 8 == 0, "gemm: lda=%d must be >= K and a multiple of 8", g.lda);
+  }
+  TAPIR_CHECK_ARG(g.out_f32 != nullptr || g.out_planes != nullptr, "gemm: no output");
+  if (g.out_planes != nullptr)
+    TAPIR_CHECK_ARG(g.out_P >= 1 && g.out_P <= 3 && g.ldp >= g.N, "gemm: bad plane output (out_P=%d ldp=%d)", g.out_P, g.ldp);
+  if (g.out_f32 != nullptr) TAPIR_CHECK_ARG(g.ldo >= g.N, "gemm: ldo=%d < N=%d", g.ldo, g.N);
+  if (g.residual != nullptr) TAPIR_CHECK_ARG(g.ldr >= g.N, "gemm: ldr=%d < N=%d", g.ldr, g.N);
+  return kOk;
+}
+
+int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
+  TAPIR_RETURN_IF(validate_gemm_args(g));
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M;
+  p.N = g.N;
+  p.num_k_blocks = g.K / kBlockK;
+  p.mode = g.mode;
+  p.bias = g.bias;
+  p.residual = g.residual;
+  p.ldr = g.ldr;
+  p.act = g.act;
+  p.out_f32 = g.out_f32;
+  p.ldo = g.ldo;
+  p.out_planes = g.out_planes;
+  p.ldp = g.ldp;
+  p.out_plane_stride = g.out_plane_stride;
+  p.out_P = g.out_P;
+  p.err = device_error_flag();
+  const int P = g.planes;
+
+  if (g.mode == kGemmConv3x3) {
+    choose_conv_tile(g.H, g.W, &p.tileW, &p.tileH);
+    p.H = g.H;
+    p.W = g.W;
+    p.cblocks = g.C / kBlockK;
+    p.tiles_x = ceil_div(g.W, p.tileW);
+    p.tiles_y = ceil_div(g.H, p.tileH);
+    p.num_m_tiles = g.frames * p.tiles_x * p.tiles_y;
+    const long long plane = g.a_plane_stride > 0 ? g.a_plane_stride : (long long)g.M * g.C;
+    cuuint64_t dims[5] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.frames, (cuuint64_t)P};
+    cuuint64_t str[4] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2,
+                         (cuuint64_t)plane * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)p.tileW, (cuuint32_t)p.tileH, 1, 1};
+    TAPIR_RETURN_IF(encode_bf16_map(&p.tmA, g.a, 5, dims, str, box, "A/conv"));
+  } else {
+    p.num_m_tiles = ceil_div(g.M, kBlockM);
+    const long long plane = g.a_plane_stride > 0 ? g.a_plane_stride : (long long)g.M * g.lda;
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.M, (cuuint64_t)P};
+    cuuint64_t str[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)plane * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)kBlockM, 1};
+    TAPIR_RETURN_IF(encode_bf16_map(&p.tmA, g.a, 3, dims, str, box, "A"));
+  }
+  const int bn = pick_block_n(p.num_m_tiles, g.N, P);
+  p.num_n_tiles = ceil_div(g.N, bn);
+  {
+    const long long plane = g.b_plane_stride > 0 ? g.b_plane_stride : (long long)g.N * g.ldb;
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.N, (cuuint64_t)P};
+    cuuint64_t str[2] = {(cuuint64_t)g.ldb * 2, (cuuint64_t)plane * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)bn, 1};
+    TAPIR_RETURN_IF(encode_bf16_map(&p.tmB, g.b, 3, dims, str, box, "B"));
+  }
+
+#define TAPIR_TC_CASE(BN, PP) \
+  if (bn == BN && P == PP) return launch<BN, PP>(p, stream);
+  TAPIR_TC_CASE(64, 1) TAPIR_TC_CASE(64, 2) TAPIR_TC_CASE(64, 3)
+  TAPIR_TC_CASE(128, 1) TAPIR_TC_CASE(128, 2) TAPIR_TC_CASE(128, 3)
+  TAPIR_TC_CASE(256, 1) TAPIR_TC_CASE(256, 2)
+#undef TAPIR_TC_CASE
+  set_error("gemm_tc: no kernel for BLOCK_N=%d planes=%d", bn, P);
+  return kUnsupported;
+}
+
+}  // namespace tapir

@@ -1,0 +1,572 @@
+// Refinement loop kernels: pyramid pooling, fused bilinear-sample +
+// dot local correlation (which also assembles the mixer input row), the depthwise-conv half
+// of each PIPs mixer block, the mixer orchestration around the tcgen05 GEMMs, and the
+// residual update.
+#include "kernels.cuh"
+
+namespace tapir {
+
+namespace {
+
+// ------------------------------------------------------------------------ a9 pooling
+// tapir_model.py:519-527 avg_pool3d(kernel (2,2,1)) on [T,h,w,C] -> [T,h/2,w/2,C].
+__global__ void __launch_bounds__(256) pool_kernel(const float4* __restrict__ in, int h, int w,
+                                                   int c4n, float4* __restrict__ out,
+                                                   long long total) {
+  const int oh = h / 2, ow = w / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % c4n);
+    long long r = i / c4n;
+    const int ox = (int)(r % ow);
+    r /= ow;
+    const int oy = (int)(r % oh);
+    const long long t = r / oh;
+    const long long base = ((t * h + 2 * oy) * w + 2 * ox) * c4n + g;
+    const float4 a = in[base], b = in[base + c4n], c = in[base + (long long)w * c4n],
+                 d = in[base + (long long)w * c4n + c4n];
+    out[i] = make_float4((((a.x + b.x) + c.x) + d.x) * 0.25f, (((a.y + b.y) + c.y) + d.y) * 0.25f,
+                         (((a.z + b.z) + c.z) + d.z) * 0.25f, (((a.w + b.w) + c.w) + d.w) * 0.25f);
+  }
+}
+
+// ------------------------------------------------------------------------ a7 local correlation
+// tapir_model.py:599-658 + utils.py:76-113.  For every (query n, frame t) and pyramid level:
+//   c = pos * (gw, gh) / (init_w, init_h)              (grid coordinates, x then y)
+//   49 samples at (y + dy, x + dx), dy, dx in -3..3, bilinear, zeros padding, where
+//   grid_sample sees g = 2*(c / gh) - 1 for BOTH axes (the reference divides x by h too), so
+//   the sampled pixel is  iy = ((2*(cy/gh)-1 + 1)*gh - 1)/2,  ix = ((2*(cx/gh)-1 + 1)*gw - 1)/2.
+//   corr[s] = <bilinear patch feature, query feature>.
+// Because the dot product is linear, we first dot every CELL of the bounding box of the 49
+// samples with the query (one coalesced C-vector load per cell, 8 rows x <=16 columns), then
+// combine 4 cell dots per sample with its bilinear weights: 64*C MACs instead of 196*C.
+// One warp per level; the CTA (one (n,t) row) then writes the whole mixer input row
+// [0, 0, occ, expd, feat(384), corr(49*L), 0-pad] as bf16 planes.
+constexpr int kBoxRows = 8;
+constexpr int kBoxColsMax = 16;
+constexpr int kBoxCells = kBoxRows * kBoxColsMax;
+
+struct CorrParams {
+  tapir_corr_args a;
+};
+
+template <int V>  // V = C / 128 float4 per lane
+__device__ __forceinline__ void cell_dots(const float* __restrict__ frame, int gh, int gw, int y0,
+                                          int x0, int box_w, const float4 (&q)[V],
+                                          float* __restrict__ table, int lane) {
+  // cells are processed in groups of 32 (box index b = row * box_w + col)
+  const int C = V * 128;
+  const int ncell = kBoxRows * box_w;
+  for (int b0 = 0; b0 < ncell; b0 += 32) {
+    float part[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int b = b0 + j;
+      const int r = b / box_w, c = b - r * box_w;
+      const int y = y0 + r, x = x0 + c;
+      float acc = 0.f;
+      if (b < ncell && y >= 0 && y < gh && x >= 0 && x < gw) {
+        const float4* cp = reinterpret_cast<const float4*>(frame + ((long long)y * gw + x) * C);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float4 f = __ldg(cp + v * 32 + lane);
+          acc = fmaf(f.x, q[v].x, acc);
+          acc = fmaf(f.y, q[v].y, acc);
+          acc = fmaf(f.z, q[v].z, acc);
+          acc = fmaf(f.w, q[v].w, acc);
+        }
+      }
+      part[j] = acc;
+    }
+    // transpose-reduce: afterwards lane l holds the full dot product of cell b0 + l
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int j = 0; j < s; ++j) {
+        const bool up = (lane & s) != 0;
+        const float send = up ? part[j] : part[j + s];
+        const float keep = up ? part[j + s] : part[j];
+        part[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+    if (b0 + lane < kBoxCells) table[b0 + lane] = part[0];
+  }
+}
+
+__global__ void __launch_bounds__(96) local_corr_kernel(const CorrParams p) {
+  __shared__ float table[TAPIR_MAX_CORR_LEVELS][kBoxCells];
+  __shared__ float corr[TAPIR_MAX_CORR_LEVELS * 49];
+  const tapir_corr_args& a = p.a;
+  const int T = a.num_frames;
+  const long long row = blockIdx.x;
+  const int n = (int)(row / T), t = (int)(row - (long long)n * T);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float px = a.pos[row * 2 + 0], py = a.pos[row * 2 + 1];
+  const float* fhi = a.feat_hi + n * a.feat_hi_stride_n + t * a.feat_hi_stride_t;
+  const float* flo = a.feat_lo + n * a.feat_lo_stride_n + t * a.feat_lo_stride_t;
+
+  if (warp < a.num_levels) {
+    const tapir_corr_level& L = a.levels[warp];
+    const int gh = L.h, gw = L.w;
+    // utils.convert_grid_coordinates (coords * out / in), tapir_model.py:603-606
+    const float cx = __fdiv_rn(__fmul_rn(px, (float)gw), (float)a.init_w);
+    const float cy = __fdiv_rn(__fmul_rn(py, (float)gh), (float)a.init_h);
+    // pixel-space sample position of offset d:  ((2*((c+d)/gh) - 1 + 1) * size - 1) / 2
+    auto pix = [&](float c, int d, int size) {
+      const float g = __fsub_rn(__fmul_rn(2.f, __fdiv_rn(__fadd_rn(c, (float)d), (float)gh)), 1.f);
+      return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), 1.f), 2.f);
+    };
+    const int y0 = (int)floorf(pix(cy, -3, gh));
+    const int x0 = (int)floorf(pix(cx, -3, gw));
+    const int x_last = (int)floorf(pix(cx, 3, gw)) + 1;
+    int box_w = x_last - x0 + 1;
+    if (box_w > kBoxColsMax) box_w = kBoxColsMax;  // host guarantees gw/gh <= 2 (see local_corr)
+    if (box_w < 2) box_w = 2;
+    const float* frame = L.grid + (long long)t * gh * gw * L.C;
+    if (L.C == 128) {
+      float4 q[1];
+      q[0] = reinterpret_cast<const float4*>(fhi)[lane];
+      cell_dots<1>(frame, gh, gw, y0, x0, box_w, q, table[warp], lane);
+    } else {
+      float4 q[2];
+      q[0] = reinterpret_cast<const float4*>(flo)[lane];
+      q[1] = reinterpret_cast<const float4*>(flo)[32 + lane];
+      cell_dots<2>(frame, gh, gw, y0, x0, box_w, q, table[warp], lane);
+    }
+    __syncwarp();
+    for (int sidx = lane; sidx < 49; sidx += 32) {
+      const int dy = sidx / 7 - 3, dx = sidx % 7 - 3;
+      const float iy = pix(cy, dy, gh), ix = pix(cx, dx, gw);
+      const float fy0 = floorf(iy), fx0 = floorf(ix);
+      const int ry = (int)fy0 - y0, rx = (int)fx0 - x0;
+      // ATen grid_sampler bilinear weights
+      const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+      const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
+      // a corner can fall outside the box only through fp jitter at an exactly-integer
+      // sample position, where its weight is ~1e-7: treating it as 0 is exact to fp32 noise
+      const float* tb = table[warp];
+      auto cell = [&](int r, int c) {
+        return (r >= 0 && r < kBoxRows && c >= 0 && c < box_w) ? tb[r * box_w + c] : 0.f;
+      };
+      const float v = cell(ry, rx) * (wx0 * wy0) + cell(ry, rx + 1) * (wx1 * wy0) +
+                      cell(ry + 1, rx) * (wx0 * wy1) + cell(ry + 1, rx + 1) * (wx1 * wy1);
+      corr[warp * 49 + sidx] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- assemble the mixer input row (tapir_model.py:647-658), split into bf16 planes
+  const int ncorr = 49 * a.num_levels;
+  const float occ = a.occ[row], expd = a.expd[row];
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out_planes);
+  for (int e = threadIdx.x; e < a.ld; e += blockDim.x) {
+    float v;
+    if (e < 2) v = 0.f;  // position slots are zeroed (tapir_model.py:647)
+    else if (e == 2) v = occ;
+    else if (e == 3) v = expd;
+    else if (e < 4 + 128) v = fhi[e - 4];
+    else if (e < 4 + 384) v = flo[e - 132];
+    else if (e < 388 + ncorr) v = corr[e - 388];
+    else v = 0.f;
+    for (int q = 0; q < a.planes; ++q) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      v -= __bfloat162float(h);
+      out[q * a.out_plane_stride + row * a.ld + e] = h;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ a8 depthwise half
+// nets.py:143-181 for one PIPsConvBlock, everything before the channel MLP:
+//   y  = LN(x) * w                                   (scale only, eps 1e-5)
+//   h1 = gelu(dwconv_k3(y; 512 -> 2048, 4 per channel) + b1)
+//   h2 = dwconv_k3(h1; 2048) + b2 ;  z = x + sum of the 4 multipliers
+//   out: z (fp32) and LN_1(z) * w1 as bf16 planes (the A operand of the `up` GEMM).
+// Non-causal convs zero-pad one frame each side; causal convs look 2 frames back, with
+// the optional context (last 2 frames of y and of h1 from the previous call) standing in for
+// frames -2, -1 (nets.py:149-176).  CTA = one query, `kDwTile` output frames; thread = one of
+// the 512 channels.
+constexpr int kDwTile = 24;
+constexpr int kDwHalo = 4;
+constexpr int kDwRows = kDwTile + kDwHalo;
+
+struct DwParams {
+  const float* x;
+  float* z;
+  __nv_bfloat16* planes_out;
+  long long plane_stride;
+  int planes;
+  int T;
+  int causal;
+  const float* ln_w;
+  const float* w1;
+  const float* b1;
+  const float* w2;
+  const float* b2;
+  const float* ln1_w;
+  const float* ctx1_in;
+  const float* ctx2_in;
+  float* ctx1_out;
+  float* ctx2_out;
+};
+
+__global__ void __launch_bounds__(512) mixer_dw_kernel(const DwParams p) {
+  extern __shared__ float dw_smem[];  // [kDwRows][512] LN'd rows, later reused for z
+  const int n = blockIdx.y;
+  const int t0 = blockIdx.x * kDwTile;
+  const int t1 = min(t0 + kDwTile, p.T);
+  const int c = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // y rows needed: non-causal t0-2 .. t1+1 ; causal t0-4 .. t1-1.  smem row r <-> frame lo + r.
+  const int lo = p.causal ? t0 - 4 : t0 - 2;
+  const int hi = p.causal ? t1 : t1 + 2;  // exclusive
+  const float* xn = p.x + (long long)n * p.T * 512;
+
+  for (int r = warp; r < hi - lo; r += 16) {
+    const int t = lo + r;
+    float* dst = dw_smem + r * 512;
+    if (t >= 0 && t < p.T) {
+      const float4* xr = reinterpret_cast<const float4*>(xn + (long long)t * 512);
+      float4 v[4];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[i] = xr[i * 32 + lane];
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+      }
+      const float mean = warp_sum(s) * (1.0f / 512);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        ss += a * a + b * b + cc * cc + d * d;
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(ss) * (1.0f / 512) + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 ww = reinterpret_cast<const float4*>(p.ln_w)[i * 32 + lane];
+        reinterpret_cast<float4*>(dst)[i * 32 + lane] =
+            make_float4((v[i].x - mean) * rstd * ww.x, (v[i].y - mean) * rstd * ww.y,
+                        (v[i].z - mean) * rstd * ww.z, (v[i].w - mean) * rstd * ww.w);
+      }
+    } else if (p.causal && p.ctx1_in != nullptr && t >= -2 && t < 0) {
+      // context frames -2, -1 of the layer-normed input
+      const float4* cr = reinterpret_cast<const float4*>(p.ctx1_in + ((long long)n * 2 + (t + 2)) * 512);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i * 32 + lane] = cr[i * 32 + lane];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i * 32 + lane] = make_float4(0, 0, 0, 0);
+    }
+  }
+  __syncthreads();
+
+  // per-channel weights: 4 multipliers x 3 taps for both convs
+  float w1[4][3], w2[4][3], b1[4], b2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    b1[j] = p.b1[4 * c + j];
+    b2[j] = p.b2[4 * c + j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      w1[j][k] = p.w1[(4 * c + j) * 3 + k];
+      w2[j][k] = p.w2[(4 * c + j) * 3 + k];
+    }
+  }
+  auto yv = [&](int t) { return dw_smem[(t - lo) * 512 + c]; };
+  // h1 at frame t (0 outside the sequence; context for frames -2,-1 in causal mode)
+  auto h1 = [&](int t, float (&o)[4]) {
+    if (t >= 0 && t < p.T) {
+      const int base = p.causal ? t - 2 : t - 1;
+      const float a0 = yv(base), a1 = yv(base + 1), a2 = yv(base + 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o[j] = gelu_tanh(fmaf(w1[j][2], a2, fmaf(w1[j][1], a1, fmaf(w1[j][0], a0, b1[j]))));
+    } else if (p.causal && p.ctx2_in != nullptr && t >= -2 && t < 0) {
+      const float4 v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + (t + 2)) * 2048 + 4 * c);
+      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    } else {
+      o[0] = o[1] = o[2] = o[3] = 0.f;
+    }
+  };
+
+  float ha[4], hb[4], hc[4];  // sliding window of h1 over 3 consecutive frames
+  const int first = p.causal ? t0 - 2 : t0 - 1;
+  h1(first, ha);
+  h1(first + 1, hb);
+  float zreg[kDwTile];
+#pragma unroll
+  for (int i = 0; i < kDwTile; ++i) {
+    const int t = t0 + i;
+    if (t < t1) {
+      h1(first + 2 + i, hc);
+      float acc = xn[(long long)t * 512 + c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        acc += fmaf(w2[j][2], hc[j], fmaf(w2[j][1], hb[j], fmaf(w2[j][0], ha[j], b2[j])));
+      zreg[i] = acc;
+      // new causal context (last two frames of [ctx | y] and [ctx | h1], nets.py:153,167)
+      if (p.causal && p.ctx2_out != nullptr && t >= p.T - 2) {
+        // frame t's own h1 is hc (causal window = frames t-2, t-1, t)
+        *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + (t - (p.T - 2))) * 2048 + 4 * c) =
+            make_float4(hc[0], hc[1], hc[2], hc[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ha[j] = hb[j]; hb[j] = hc[j]; }
+    }
+  }
+  if (p.causal && p.ctx1_out != nullptr) {
+    for (int t = max(t0, p.T - 2); t < t1; ++t) p.ctx1_out[((long long)n * 2 + (t - (p.T - 2))) * 512 + c] = yv(t);
+    if (p.T == 1 && t0 == 0) {
+      // sequence shorter than the context: slot 0 <- old context frame -1
+      p.ctx1_out[((long long)n * 2 + 0) * 512 + c] = (p.ctx1_in != nullptr) ? p.ctx1_in[((long long)n * 2 + 1) * 512 + c] : 0.f;
+      if (p.ctx2_out != nullptr) {
+        float4 v = make_float4(0, 0, 0, 0);
+        if (p.ctx2_in != nullptr) v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + 1) * 2048 + 4 * c);
+        *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + 0) * 2048 + 4 * c) = v;
+      }
+    }
+  }
+  __syncthreads();  // everyone is done reading y from smem
+#pragma unroll
+  for (int i = 0; i < kDwTile; ++i) {
+    const int t = t0 + i;
+    if (t < t1) {
+      dw_smem[i * 512 + c] = zreg[i];
+      p.z[((long long)n * p.T + t) * 512 + c] = zreg[i];
+    }
+  }
+  __syncthreads();
+  // LN_1 (scale only) -> bf16 planes
+  for (int r = warp; r < t1 - t0; r += 16) {
+    const float4* zr = reinterpret_cast<const float4*>(dw_smem + r * 512);
+    float4 v[4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = zr[i * 32 + lane];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(s) * (1.0f / 512);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      ss += a * a + b * b + cc * cc + d * d;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(ss) * (1.0f / 512) + 1e-5f);
+    const long long orow = (long long)n * p.T + t0 + r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 ww = reinterpret_cast<const float4*>(p.ln1_w)[i * 32 + lane];
+      float o[4] = {(v[i].x - mean) * rstd * ww.x, (v[i].y - mean) * rstd * ww.y,
+                    (v[i].z - mean) * rstd * ww.z, (v[i].w - mean) * rstd * ww.w};
+      for (int q = 0; q < p.planes; ++q) {
+        __nv_bfloat16 h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h[e] = __float2bfloat16_rn(o[e]);
+          o[e] -= __bfloat162float(h[e]);
+        }
+        uint2 pk;
+        pk.x = pack_bf16x2(h[0], h[1]);
+        pk.y = pack_bf16x2(h[2], h[3]);
+        *reinterpret_cast<uint2*>(p.planes_out + q * p.plane_stride + orow * 512 + (i * 32 + lane) * 4) = pk;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ a7 epilogue
+__global__ void __launch_bounds__(128) refine_update_kernel(const tapir_update_args a) {
+  const long long row = blockIdx.x;
+  const int T = a.num_frames;
+  const int n = (int)(row / T), t = (int)(row - (long long)n * T);
+  const float* res = a.res + row * a.ld_res;
+  const float* fhi = a.feat_hi + n * a.feat_hi_stride_n + t * a.feat_hi_stride_t;
+  const float* flo = a.feat_lo + n * a.feat_lo_stride_n + t * a.feat_lo_stride_t;
+  for (int e = threadIdx.x; e < 384; e += blockDim.x) {
+    const float f = (e < 128) ? fhi[e] : flo[e - 128];
+    a.feat_out[row * 384 + e] = res[4 + e] + f;
+  }
+  if (threadIdx.x == 0) {
+    // tapir_model.py:674-682: delta is in resized-resolution pixels -> initial_resolution
+    const float dx = __fdiv_rn(__fmul_rn(res[0], (float)a.init_w), (float)a.resize_w);
+    const float dy = __fdiv_rn(__fmul_rn(res[1], (float)a.init_h), (float)a.resize_h);
+    const float x = dx + a.pos[row * 2 + 0], y = dy + a.pos[row * 2 + 1];
+    a.pos[row * 2 + 0] = x;
+    a.pos[row * 2 + 1] = y;
+    a.occ_out[row] = res[2] + a.occ_in[row];
+    a.expd_out[row] = res[3] + a.expd_in[row];
+    if (a.tracks_out != nullptr) {
+      // train2orig (tapir_model.py:435-441)
+      a.tracks_out[row * 2 + 0] = __fdiv_rn(__fmul_rn(x, (float)a.video_w), (float)a.init_w);
+      a.tracks_out[row * 2 + 1] = __fdiv_rn(__fmul_rn(y, (float)a.video_h), (float)a.init_h);
+    }
+  }
+}
+
+int grid_for(long long total, int block = 256) {
+  long long g = ceil_div_ll(total, block);
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+int pool_pyramid(const float* grid, int T, int h, int w, int C, float* out, cudaStream_t s) {
+  TAPIR_CHECK_ARG(grid && out && T > 0 && h >= 2 && w >= 2 && C % 4 == 0, "pool_pyramid: bad arguments");
+  const long long total = (long long)T * (h / 2) * (w / 2) * (C / 4);
+  pool_kernel<<<grid_for(total), 256, 0, s>>>(reinterpret_cast<const float4*>(grid), h, w, C / 4,
+                                             reinterpret_cast<float4*>(out), total);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("pool_kernel");
+  return kOk;
+}
+
+int local_corr(const tapir_corr_args* a, cudaStream_t s) {
+  TAPIR_CHECK_ARG(a != nullptr && a->num_levels >= 1 && a->num_levels <= TAPIR_MAX_CORR_LEVELS,
+                  "local_corr: bad level count");
+  TAPIR_CHECK_ARG(a->planes >= 1 && a->planes <= 3 && a->num_points > 0 && a->num_frames > 0,
+                  "local_corr: bad shape");
+  TAPIR_CHECK_ARG(a->ld >= 388 + 49 * a->num_levels && a->ld % 8 == 0, "local_corr: ld=%d too small", a->ld);
+  for (int l = 0; l < a->num_levels; ++l) {
+    const tapir_corr_level& L = a->levels[l];
+    TAPIR_CHECK_ARG(L.grid != nullptr && (L.C == 128 || L.C == 256), "local_corr: level %d C=%d unsupported", l, L.C);
+    TAPIR_CHECK_ARG((l == 0) == (L.C == 128), "local_corr: level 0 must be the 128-ch hires grid, others 256-ch");
+    // x spacing of the 49 samples is gw/gh cells (reference quirk); the cell box holds 16 columns
+    TAPIR_CHECK_ARG(7.0 * L.w / L.h + 2.0 <= kBoxColsMax, "local_corr: aspect ratio w/h=%d/%d too wide", L.w, L.h);
+  }
+  CorrParams p;
+  p.a = *a;
+  const long long rows = (long long)a->num_points * a->num_frames;
+  local_corr_kernel<<<(unsigned)rows, 96, 0, s>>>(p);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("local_corr_kernel");
+  return kOk;
+}
+
+int refine_update(const tapir_update_args* a, cudaStream_t s) {
+  TAPIR_CHECK_ARG(a != nullptr && a->res && a->pos && a->feat_out && a->occ_out && a->expd_out,
+                  "refine_update: null pointer");
+  const long long rows = (long long)a->num_points * a->num_frames;
+  refine_update_kernel<<<(unsigned)rows, 128, 0, s>>>(*a);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("refine_update_kernel");
+  return kOk;
+}
+
+// ------------------------------------------------------------------------ mixer orchestration
+
+namespace {
+struct MixerPlan {
+  float* xa;   // residual stream [rows][512]
+  float* xb;
+  __nv_bfloat16* y;  // [P][rows][512]
+  __nv_bfloat16* h;  // [P][rows][2048]
+};
+size_t plan_mixer(Arena& a, long long rows, int planes, MixerPlan* m) {
+  m->xa = a.take<float>((size_t)rows * 512);
+  m->xb = a.take<float>((size_t)rows * 512);
+  m->y = a.take<__nv_bfloat16>((size_t)rows * 512 * planes);
+  m->h = a.take<__nv_bfloat16>((size_t)rows * 2048 * planes);
+  return a.off;
+}
+GemmArgs lin(const tapir_linear& l) {
+  GemmArgs g;
+  g.planes = l.planes;
+  g.N = l.N;
+  g.K = l.K;
+  g.b = static_cast<const __nv_bfloat16*>(l.w);
+  g.ldb = l.K;
+  g.b_plane_stride = (long long)l.N * l.K;
+  g.bias = l.bias;
+  return g;
+}
+}  // namespace
+
+size_t mixer_workspace_bytes(long long rows, int planes) {
+  Arena a(nullptr, 0);
+  MixerPlan m;
+  return plan_mixer(a, rows, planes, &m) + 256;
+}
+
+int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* ws, size_t ws_bytes,
+                  cudaStream_t s) {
+  TAPIR_CHECK_ARG(w && io && io->x_planes && io->out, "mixer_forward: null pointer");
+  const int P = w->planes;
+  const int n = io->num_points, T = io->num_frames;
+  const long long rows = (long long)n * T;
+  TAPIR_CHECK_ARG(n > 0 && T > 0 && n <= 65535, "mixer_forward: bad shape n=%d T=%d", n, T);
+  TAPIR_CHECK_ARG(w->num_blocks >= 1 && w->num_blocks <= TAPIR_MAX_MIXER_BLOCKS, "mixer_forward: num_blocks");
+  TAPIR_CHECK_ARG(io->ldx == w->linear.K, "mixer_forward: ldx=%d must equal the padded input width %d", io->ldx, w->linear.K);
+  TAPIR_CHECK_ARG(io->ldo >= w->linear_1.N, "mixer_forward: ldo too small");
+  Arena arena(ws, ws_bytes);
+  MixerPlan m;
+  plan_mixer(arena, rows, P, &m);
+  if (!arena.ok) {
+    set_error("mixer_forward: workspace too small (%zu < %zu)", ws_bytes, arena.off);
+    return kWorkspaceTooSmall;
+  }
+  static bool configured = false;
+  const int dw_smem = kDwRows * 512 * (int)sizeof(float);
+  if (!configured) {
+    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    configured = true;
+  }
+  {  // nets.py:235 linear
+    GemmArgs g = lin(w->linear);
+    g.M = (int)rows;
+    g.a = static_cast<const __nv_bfloat16*>(io->x_planes);
+    g.lda = io->ldx;
+    g.a_plane_stride = io->x_plane_stride;
+    g.out_f32 = m.xa; g.ldo = 512;
+    TAPIR_RETURN_IF(gemm(g, s));
+  }
+  for (int b = 0; b < w->num_blocks; ++b) {
+    const tapir_mixer_block& blk = w->blocks[b];
+    DwParams d;
+    d.x = m.xa; d.z = m.xb;
+    d.planes_out = m.y; d.plane_stride = rows * 512; d.planes = P;
+    d.T = T; d.causal = io->causal;
+    d.ln_w = blk.ln_w; d.w1 = blk.dw1_w; d.b1 = blk.dw1_b; d.w2 = blk.dw2_w; d.b2 = blk.dw2_b;
+    d.ln1_w = blk.ln1_w;
+    d.ctx1_in = io->ctx1_in ? io->ctx1_in[b] : nullptr;
+    d.ctx2_in = io->ctx2_in ? io->ctx2_in[b] : nullptr;
+    d.ctx1_out = io->ctx1_out ? io->ctx1_out[b] : nullptr;
+    d.ctx2_out = io->ctx2_out ? io->ctx2_out[b] : nullptr;
+    dim3 grid(ceil_div(T, kDwTile), n);
+    mixer_dw_kernel<<<grid, 512, dw_smem, s>>>(d);
+    count_launch();
+    TAPIR_LAUNCH_CHECK("mixer_dw_kernel");
+    {
+      GemmArgs g = lin(blk.up);
+      g.M = (int)rows;
+      g.a = m.y; g.lda = 512; g.a_plane_stride = rows * 512;
+      g.act = 1;
+      g.out_planes = m.h; g.ldp = 2048; g.out_plane_stride = rows * 2048; g.out_P = P;
+      TAPIR_RETURN_IF(gemm(g, s));
+    }
+    {
+      GemmArgs g = lin(blk.down);
+      g.M = (int)rows;
+      g.a = m.h; g.lda = 2048; g.a_plane_stride = rows * 2048;
+      g.residual = m.xb; g.ldr = 512;
+      g.out_f32 = m.xa; g.ldo = 512;
+      TAPIR_RETURN_IF(gemm(g, s));
+    }
+  }
+  TAPIR_RETURN_IF(layernorm_split(m.xa, rows, 512, w->ln_w, nullptr, nullptr, m.y, rows * 512, P, s));
+  {
+    GemmArgs g = lin(w->linear_1);
+    g.M = (int)rows;
+    g.a = m.y; g.lda = 512; g.a_plane_stride = rows * 512;
+    g.out_f32 = io->out; g.ldo = io->ldo;
+    TAPIR_RETURN_IF(gemm(g, s));
+  }
+  return kOk;
+}
+
+}  // namespace tapir

@@ -1,0 +1,392 @@
+// Stage A (SURVEY.md 8(a4),(a6)): query-feature sampling, global cost volume and the
+// track / occlusion head.
+//
+// The cost volume itself is the split-bf16 tcgen05 GEMM (planes=3, i.e. fp32-equivalent,
+// because its arg-max must match the reference bit-exactly): cv[n][t*h*w + cell] with
+// M = queries, N = T*h*w cells, K = 256.  `cost_volume_head_kernel` then consumes one
+// 32x32 map per CTA entirely from shared memory: conv3x3 1->16 + ReLU, conv3x3 16->1,
+// temperature soft-max, arg-max, radius-5 soft arg-max, and the occlusion branch
+// (pad(0,2,0,2), conv3x3 stride 2 16->32 + ReLU, spatial mean, 32->16->2 MLP).
+#include <cfloat>
+
+#include "kernels.cuh"
+
+namespace tapir {
+
+namespace {
+
+// ------------------------------------------------------------------------ a4
+// utils.py:45-73 map_coordinates_3d: grid_sample(5-D, bilinear, align_corners=False,
+// padding_mode='border') at (t+0.5, y, x) / (T, h, w).  We mirror ATen's arithmetic:
+// g = 2*(c/size) - 1 ; pix = ((g + 1) * size - 1) / 2 ; clamp to [0, size-1].
+__device__ __forceinline__ float unnormalize_border(float c, int size) {
+  const float fs = (float)size;
+  const float g = __fsub_rn(__fmul_rn(2.f, __fdiv_rn(c, fs)), 1.f);
+  float pix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), fs), 1.f), 2.f);
+  pix = fminf(fmaxf(pix, 0.f), fs - 1.f);
+  return pix;
+}
+
+__global__ void __launch_bounds__(128) sample_query_kernel(const float* __restrict__ grid, int T,
+                                                           int gh, int gw, int C,
+                                                           const float* __restrict__ q, int vT,
+                                                           int vH, int vW, float* __restrict__ out) {
+  const int n = blockIdx.x;
+  // utils.convert_grid_coordinates: coords * out / in (tapir_model.py:266-277)
+  float t = __fdiv_rn(__fmul_rn(q[n * 3 + 0], (float)T), (float)vT);
+  const float y = __fdiv_rn(__fmul_rn(q[n * 3 + 1], (float)gh), (float)vH);
+  const float x = __fdiv_rn(__fmul_rn(q[n * 3 + 2], (float)gw), (float)vW);
+  t = __fadd_rn(t, 0.5f);
+  const float pt = unnormalize_border(t, T), py = unnormalize_border(y, gh), px = unnormalize_border(x, gw);
+  const int t0 = (int)floorf(pt), y0 = (int)floorf(py), x0 = (int)floorf(px);
+  const float ft = pt - t0, fy = py - y0, fx = px - x0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int dt = 0; dt < 2; ++dt)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int tt = t0 + dt, yy = y0 + dy, xx = x0 + dx;
+          const float wgt = (dt ? ft : 1.f - ft) * (dy ? fy : 1.f - fy) * (dx ? fx : 1.f - fx);
+          if (tt < T && yy < gh && xx < gw && tt >= 0 && yy >= 0 && xx >= 0)
+            acc += wgt * grid[(((long long)tt * gh + yy) * gw + xx) * C + c];
+        }
+    out[(long long)n * C + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------ a6 head
+constexpr int kG = 32;            // cost-volume map side (initial_resolution 256 / stride 8)
+constexpr int kOccW = kG + 3;     // 35: index -1 .. 33 (1 left halo for hid2, 2 right for hid3)
+constexpr int kOccPlane = kOccW * kOccW;
+
+struct HeadSmem {
+  float cv[(kG + 2) * (kG + 2)];     // zero-padded cost map
+  float occ[16 * kOccPlane];         // ReLU(hid1) with halo, channel-major
+  float w3[16 * 9 * 32];             // hid3 weights as [ci][tap][co]
+  float heat[kG * kG];
+  float w1[16 * 9], b1[16], w2[16 * 9], b3[32];
+  float w4[16 * 32], b4[16], w5[2 * 16], b5[2];
+  float red_f[8 * 4];
+  int red_i[8];
+  float mean32[8][32];
+  float bcast[4];
+  int bcast_i;
+};
+
+__device__ __forceinline__ void block_reduce_max_first(float v, int idx, HeadSmem& sm, float* out_v,
+                                                       int* out_i) {
+  // maximum value; among equal values the LOWEST index (torch.argmax on CPU)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { sm.red_f[warp] = v; sm.red_i[warp] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bv = sm.red_f[0];
+    int bi = sm.red_i[0];
+    for (int k = 1; k < 8; ++k)
+      if (sm.red_f[k] > bv || (sm.red_f[k] == bv && sm.red_i[k] < bi)) { bv = sm.red_f[k]; bi = sm.red_i[k]; }
+    sm.bcast[0] = bv;
+    sm.bcast_i = bi;
+  }
+  __syncthreads();
+  *out_v = sm.bcast[0];
+  *out_i = sm.bcast_i;
+}
+
+__device__ __forceinline__ void block_reduce_sum3(float a, float b, float c, HeadSmem& sm, float* oa,
+                                                  float* ob, float* oc) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { sm.red_f[warp * 4] = a; sm.red_f[warp * 4 + 1] = b; sm.red_f[warp * 4 + 2] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0, y = 0, z = 0;
+    for (int k = 0; k < 8; ++k) { x += sm.red_f[k * 4]; y += sm.red_f[k * 4 + 1]; z += sm.red_f[k * 4 + 2]; }
+    sm.bcast[0] = x; sm.bcast[1] = y; sm.bcast[2] = z;
+  }
+  __syncthreads();
+  *oa = sm.bcast[0]; *ob = sm.bcast[1]; *oc = sm.bcast[2];
+}
+
+__global__ void __launch_bounds__(256) cost_volume_head_kernel(
+    const tapir_head_weights w, const float* __restrict__ cost_volume, int T,
+    const float* __restrict__ query_tyx, float temperature, int init_h, int init_w,
+    float* __restrict__ points, float* __restrict__ occ_out, float* __restrict__ expd_out,
+    int* __restrict__ argmax_out) {
+  extern __shared__ __align__(16) uint8_t head_smem_raw[];
+  HeadSmem& sm = *reinterpret_cast<HeadSmem*>(head_smem_raw);
+  const int t = blockIdx.x, n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const float* cv = cost_volume + ((long long)n * T + t) * (kG * kG);
+
+  // ---- stage weights and the zero-padded map
+  for (int i = tid; i < (kG + 2) * (kG + 2); i += 256) sm.cv[i] = 0.f;
+  for (int i = tid; i < 16 * kOccPlane; i += 256) sm.occ[i] = 0.f;
+  for (int i = tid; i < 16 * 9 * 32; i += 256) {
+    const int co = i & 31, tap = (i >> 5) % 9, ci = i / (32 * 9);
+    sm.w3[i] = w.hid3_w[(co * 16 + ci) * 9 + tap];
+  }
+  if (tid < 144) { sm.w1[tid] = w.hid1_w[tid]; sm.w2[tid] = w.hid2_w[tid]; }
+  if (tid < 16) { sm.b1[tid] = w.hid1_b[tid]; sm.b4[tid] = w.hid4_b[tid]; }
+  if (tid < 32) { sm.b3[tid] = w.hid3_b[tid]; sm.w5[tid] = w.occ_w[tid]; }
+  if (tid < 2) sm.b5[tid] = w.occ_b[tid];
+  for (int i = tid; i < 512; i += 256) sm.w4[i] = w.hid4_w[i];
+  __syncthreads();
+  for (int i = tid; i < kG * kG; i += 256) sm.cv[((i >> 5) + 1) * (kG + 2) + (i & 31) + 1] = cv[i];
+  __syncthreads();
+
+  // ---- hid1: conv3x3 1->16 (padding 1) + ReLU.  Thread = row y, 4 consecutive x.
+  const int y = tid >> 3, x0 = (tid & 7) * 4;
+  {
+    float win[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) win[r][c] = sm.cv[(y + r) * (kG + 2) + x0 + c];
+    for (int co = 0; co < 16; ++co) {
+      float a[4] = {sm.b1[co], sm.b1[co], sm.b1[co], sm.b1[co]};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float wv = sm.w1[co * 9 + ky * 3 + kx];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) a[p] = fmaf(win[ky][kx + p], wv, a[p]);
+        }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) sm.occ[co * kOccPlane + (y + 1) * kOccW + (x0 + p + 1)] = fmaxf(a[p], 0.f);
+    }
+  }
+  __syncthreads();
+
+  // ---- hid2: conv3x3 16->1 (padding 1), x temperature
+  float heat[4];
+  {
+    const float b2 = w.hid2_b[0];
+    float a[4] = {b2, b2, b2, b2};
+    for (int ci = 0; ci < 16; ++ci) {
+      const float* op = sm.occ + ci * kOccPlane;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        float row[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) row[c] = op[(y + ky) * kOccW + x0 + c];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float wv = sm.w2[ci * 9 + ky * 3 + kx];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) a[p] = fmaf(row[kx + p], wv, a[p]);
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) heat[p] = a[p] * temperature;
+  }
+
+  // ---- softmax over the 1024 cells, argmax of the PROBABILITIES (first index on ties),
+  //      soft arg-max within radius 5 (utils.py:116-150)
+  float lmax = fmaxf(fmaxf(heat[0], heat[1]), fmaxf(heat[2], heat[3]));
+  int dummy;
+  float gmax;
+  block_reduce_max_first(lmax, 0, sm, &gmax, &dummy);
+  float e[4], lsum = 0.f;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) { e[p] = expf(heat[p] - gmax); lsum += e[p]; }
+  float gsum, u1, u2;
+  block_reduce_sum3(lsum, 0.f, 0.f, sm, &gsum, &u1, &u2);
+  float prob[4];
+  float pbest = -1.f;
+  int ibest = 0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    prob[p] = e[p] / gsum;
+    if (prob[p] > pbest) { pbest = prob[p]; ibest = y * kG + x0 + p; }
+  }
+  float pm;
+  int am;
+  block_reduce_max_first(pbest, ibest, sm, &pm, &am);
+  const float cx = (float)(am & 31) + 0.5f, cy = (float)(am >> 5) + 0.5f;
+  float sx = 0.f, sy = 0.f, sw = 0.f;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float px = (float)(x0 + p) + 0.5f, py = (float)y + 0.5f;
+    const float dx = px - cx, dy = py - cy;
+    if (dx * dx + dy * dy < 25.f) { sx += px * prob[p]; sy += py * prob[p]; sw += prob[p]; }
+  }
+  float tx, ty, tw;
+  block_reduce_sum3(sx, sy, sw, sm, &tx, &ty, &tw);
+
+  // ---- hid3: pad(0,2,0,2), conv3x3 stride 2 16->32 + ReLU; thread = one of 16x16 outputs
+  {
+    const int oy = tid >> 4, ox = tid & 15;
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = sm.b3[c];
+    for (int ci = 0; ci < 16; ++ci) {
+      const float* op = sm.occ + ci * kOccPlane + (2 * oy + 1) * kOccW + (2 * ox + 1);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = op[ky * kOccW + kx];
+          const float4* wr = reinterpret_cast<const float4*>(sm.w3 + (ci * 9 + ky * 3 + kx) * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 w4 = wr[g];
+            acc[4 * g + 0] = fmaf(v, w4.x, acc[4 * g + 0]);
+            acc[4 * g + 1] = fmaf(v, w4.y, acc[4 * g + 1]);
+            acc[4 * g + 2] = fmaf(v, w4.z, acc[4 * g + 2]);
+            acc[4 * g + 3] = fmaf(v, w4.w, acc[4 * g + 3]);
+          }
+        }
+    }
+    // spatial mean over the 256 outputs: warp-level transpose-reduce, then across 8 warps
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = fmaxf(acc[c], 0.f);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int j = 0; j < s; ++j) {
+        const bool up = (lane & s) != 0;
+        const float send = up ? acc[j] : acc[j + s];
+        const float keep = up ? acc[j + s] : acc[j];
+        acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+    sm.mean32[warp][lane] = acc[0];  // lane l holds channel l summed over the warp
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float m = 0.f;
+    for (int k = 0; k < 8; ++k) m += sm.mean32[k][tid];
+    sm.mean32[0][tid] = m * (1.0f / 256.0f);
+  }
+  __syncthreads();
+  if (tid < 16) {
+    float a = sm.b4[tid];
+    for (int k = 0; k < 32; ++k) a = fmaf(sm.mean32[0][k], sm.w4[tid * 32 + k], a);
+    sm.mean32[1][tid] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float a = sm.b5[tid];
+    for (int k = 0; k < 16; ++k) a = fmaf(sm.mean32[1][k], sm.w5[tid * 16 + k], a);
+    const long long o = (long long)n * T + t;
+    if (tid == 0) occ_out[o] = a; else expd_out[o] = a;
+  }
+  if (tid == 0) {
+    const long long o = (long long)n * T + t;
+    const float den = fmaxf(tw, 1e-12f);
+    // utils.py:165-169: cell units -> initial_resolution pixels (coords * out / in)
+    float px = __fdiv_rn(__fmul_rn(tx / den, (float)init_w), (float)kG);
+    float py = __fdiv_rn(__fmul_rn(ty / den, (float)init_h), (float)kG);
+    if (query_tyx != nullptr) {
+      // utils.py:171-191: on the query frame the track passes through the query point
+      const float qf = rintf(query_tyx[n * 3 + 0]);
+      if (qf == (float)t) { px = query_tyx[n * 3 + 2]; py = query_tyx[n * 3 + 1]; }
+    }
+    points[o * 2 + 0] = px;
+    points[o * 2 + 1] = py;
+    if (argmax_out != nullptr) argmax_out[o] = am;
+  }
+}
+
+}  // namespace
+
+int sample_query_features(const float* grid, int T, int gh, int gw, int C, const float* query_tyx,
+                          int N, int vT, int vH, int vW, float* out, cudaStream_t s) {
+  TAPIR_CHECK_ARG(grid && query_tyx && out && N > 0 && T > 0 && gh > 0 && gw > 0 && C > 0,
+                  "sample_query_features: bad arguments");
+  sample_query_kernel<<<N, 128, 0, s>>>(grid, T, gh, gw, C, query_tyx, vT, vH, vW, out);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("sample_query_kernel");
+  return kOk;
+}
+
+int cost_volume_head(const tapir_head_weights* w, const float* cost_volume, int N, int T,
+                     const float* query_tyx, float temperature, int init_h, int init_w,
+                     float* points, float* occ, float* expd, int* argmax, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(HeadSmem)));
+    configured = true;
+  }
+  TAPIR_CHECK_ARG(N <= 65535, "cost_volume_head: at most 65535 queries per call (got %d)", N);
+  dim3 grid(T, N);
+  cost_volume_head_kernel<<<grid, 256, sizeof(HeadSmem), s>>>(*w, cost_volume, T, query_tyx, temperature,
+                                                             init_h, init_w, points, occ, expd, argmax);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("cost_volume_head_kernel");
+  return kOk;
+}
+
+namespace {
+constexpr int kCvPlanes = 3;
+struct CvPlan {
+  __nv_bfloat16* q;
+  __nv_bfloat16* g;
+  float* cv;
+  int n_pad;
+};
+size_t plan_cv(Arena& a, int N, int T, int gh, int gw, int C, CvPlan* p) {
+  const long long cells = (long long)T * gh * gw;
+  p->q = a.take<__nv_bfloat16>((size_t)N * C * kCvPlanes);
+  p->g = a.take<__nv_bfloat16>((size_t)cells * C * kCvPlanes);
+  p->cv = a.take<float>((size_t)N * cells);
+  return a.off;
+}
+}  // namespace
+
+size_t cost_volume_workspace_bytes(int N, int T, int gh, int gw, int C) {
+  Arena a(nullptr, 0);
+  CvPlan p;
+  return plan_cv(a, N, T, gh, gw, C, &p) + 256;
+}
+
+int cost_volume_tracks(const tapir_head_weights* w, const float* qfeat, const float* grid, int N,
+                       int T, int gh, int gw, int C, const float* query_tyx, float temperature,
+                       int init_h, int init_w, float* points, float* occ, float* expd, int* argmax,
+                       void* ws, size_t ws_bytes, cudaStream_t s) {
+  TAPIR_CHECK_ARG(w && qfeat && grid && points && occ && expd, "cost_volume_tracks: null pointer");
+  TAPIR_CHECK_ARG(N > 0 && T > 0 && C % 64 == 0, "cost_volume_tracks: bad shape N=%d T=%d C=%d", N, T, C);
+  if (gh != kG || gw != kG) {
+    set_error("cost_volume_tracks: only a 32x32 cost-volume map (initial_resolution 256x256) is "
+              "implemented (got %dx%d)", gh, gw);
+    return kUnsupported;
+  }
+  Arena arena(ws, ws_bytes);
+  CvPlan p;
+  plan_cv(arena, N, T, gh, gw, C, &p);
+  if (!arena.ok) {
+    set_error("cost_volume_tracks: workspace too small (%zu < %zu)", ws_bytes, arena.off);
+    return kWorkspaceTooSmall;
+  }
+  const long long cells = (long long)T * gh * gw;
+  TAPIR_RETURN_IF(split_planes(qfeat, C, p.q, C, (long long)N * C, N, C, C, kCvPlanes, s));
+  TAPIR_RETURN_IF(split_planes(grid, C, p.g, C, cells * C, cells, C, C, kCvPlanes, s));
+  GemmArgs g;
+  g.planes = kCvPlanes;
+  g.M = N;
+  g.N = (int)cells;
+  g.K = C;
+  g.a = p.q; g.lda = C; g.a_plane_stride = (long long)N * C;
+  g.b = p.g; g.ldb = C; g.b_plane_stride = cells * C;
+  g.out_f32 = p.cv; g.ldo = (int)cells;
+  TAPIR_RETURN_IF(gemm(g, s));
+  return cost_volume_head(w, p.cv, N, T, query_tyx, temperature, init_h, init_w, points, occ, expd,
+                          argmax, s);
+}
+
+}  // namespace tapir

@@ -1,0 +1,90 @@
+"""End-to-end parity: CUDA path vs the reference's golden outputs and vs the CPU oracle.
+
+Tolerances are BASELINE.json's: tracks 1e-3 px, occlusion / expected_dist logits 1e-4
+(arg-max indices are checked bit-exact in test_stages_gpu.py::test_cost_volume_tracks).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import synth  # noqa: E402
+from oracle import tapir_oracle as O  # noqa: E402
+from tapnet_b200 import tapir_model  # noqa: E402
+from tests import gpu_util as U  # noqa: E402
+from tests.conftest import load_golden  # noqa: E402
+from tests.test_stages_gpu import get_model  # noqa: E402
+
+TRACK_TOL = 1e-3
+LOGIT_TOL = 1e-4
+
+
+def _inputs(meta):
+  video = synth.make_video(meta['T'], meta['H'], meta['W'], seed=meta['video_seed'])
+  q = synth.make_queries(meta['N'], meta['T'], meta['H'], meta['W'], seed=meta['query_seed'],
+                         frame0_only=(meta['mode'] == 'causal'))
+  return video, q
+
+
+@pytest.mark.parametrize('name', ['c1_bootstapir_256x8_n16', 'tapir_pl0_noextra_256x4_n8',
+                                  'bootstapir_320x384x4_n12', 'causal_256x6_n16'])
+def test_forward_matches_reference_golden(name):
+  g = load_golden(name)
+  meta = g['meta']
+  kw = meta['model_kwargs']
+  model, _, _ = get_model(kw.get('pyramid_level', 1), kw.get('extra_convs', True),
+                          kw.get('use_casual_conv', False))
+  video, q = _inputs(meta)
+  out = model(video.cuda(), q.cuda())
+  torch.cuda.synchronize()
+  e_t = np.abs(out['tracks'][0].cpu().numpy() - g['tracks']).max()
+  e_o = np.abs(out['occlusion'][0].cpu().numpy() - g['occlusion']).max()
+  e_e = np.abs(out['expected_dist'][0].cpu().numpy() - g['expected_dist']).max()
+  per_iter = [float(np.abs(t[0].cpu().numpy() - g['tracks_iters'][i]).max())
+              for i, t in enumerate(out['unrefined_tracks'])]
+  U.record(f'e2e_{name}', tracks_err=e_t, occ_err=e_o, expd_err=e_e, per_iter_tracks=str(per_iter))
+  assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_e < LOGIT_TOL
+
+
+def test_streaming_matches_reference_golden():
+  """pytorch_live_demo.py call pattern: per-frame estimate_trajectories with causal state."""
+  g = load_golden('causal_256x6_n16')
+  meta = g['meta']
+  model, _, _ = get_model(causal=True)
+  video, q = _inputs(meta)
+  video, q = video.cuda(), q.cuda()
+  g0 = model.get_feature_grids(video[:, :1], False)
+  qf0 = model.get_query_features(video[:, :1], False, q, g0)
+  state = model.construct_initial_causal_state(meta['N'], len(qf0.resolutions) - 1)
+  state = [{k: v.cuda() for k, v in d.items()} for d in state]
+  tr, oc, ex = [], [], []
+  for t in range(meta['T']):
+    gr = model.get_feature_grids(video[:, t:t + 1], False)
+    r = model.estimate_trajectories((meta['H'], meta['W']), False, gr, qf0, None, 64,
+                                    causal_context=state, get_causal_context=True)
+    state = r['causal_context']
+    tr.append(r['tracks'][-1][0].cpu().numpy())
+    oc.append(r['occlusion'][-1][0].cpu().numpy())
+    ex.append(r['expected_dist'][-1][0].cpu().numpy())
+  e_t = np.abs(np.concatenate(tr, 1) - g['online_tracks']).max()
+  e_o = np.abs(np.concatenate(oc, 1) - g['online_occlusion']).max()
+  e_e = np.abs(np.concatenate(ex, 1) - g['online_expected_dist']).max()
+  e_s = np.abs(state[-1]['block_11_causal_2'][0, :, :, ::64].cpu().numpy() - g['online_state_sub']).max()
+  U.record('e2e_streaming', tracks_err=e_t, occ_err=e_o, expd_err=e_e, state_err=e_s)
+  assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_e < LOGIT_TOL and e_s < 5e-4
+
+
+def test_chunking_and_oracle_agreement_larger():
+  """T=12, N=96 against the CPU oracle (a size the oracle finishes in seconds)."""
+  model, sd, cfg = get_model()
+  T, N = 12, 96
+  video, q = synth.make_video(T), synth.make_queries(N, T)
+  with torch.no_grad():
+    ref = O.forward(sd, cfg, video, q)
+  out = model(video.cuda(), q.cuda())
+  e_t = (out['tracks'].cpu() - ref['tracks']).abs().max().item()
+  e_o = (out['occlusion'].cpu() - ref['occlusion']).abs().max().item()
+  e_e = (out['expected_dist'].cpu() - ref['expected_dist']).abs().max().item()
+  U.record('e2e_oracle_T12_N96', tracks_err=e_t, occ_err=e_o, expd_err=e_e)
+  assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_e < LOGIT_TOL
