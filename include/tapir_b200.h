@@ -39,7 +39,7 @@ typedef struct tapir_linear {
   int32_t N;
   int32_t K;
   int32_t planes;
-  int32_t reserved;
+  int32_t k_logical; /* un-padded contraction length (profiling only; 0 = K) */
 } tapir_linear;
 
 /* nets.py:247-327 BlockV2 (InstanceNorm affine eps 1e-5). */
@@ -179,6 +179,12 @@ const char* tapir_last_error(void);
 int tapir_abi_version(void);
 /* kernels launched by this library since load (bench.py reports it as gpu_launches) */
 unsigned long long tapir_launch_count(void);
+
+/* Per-launch device timing (CUDA events on the launch stream).  tapir_profile_report
+ * synchronises the device, writes a JSON object {"kernel class": {"launches", "ms", "flops",
+ * "bytes"}} (algorithmic flops / bytes per SURVEY.md 8(d)) into buf and clears the records. */
+void tapir_profile_enable(int32_t on);
+int tapir_profile_report(char* buf, size_t capacity);
 
 /* fp32 [rows][ld_src] -> bf16 planes [planes][rows][ld_dst]; columns cols..cols_padded-1 are
  * zero filled.  Used to prepare weights and features for the GEMMs. */

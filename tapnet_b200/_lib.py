@@ -19,7 +19,7 @@ MAX_CORR_LEVELS = 3
 
 class Linear(Structure):
   _fields_ = [('w', c_void_p), ('bias', c_void_p), ('N', c_int32), ('K', c_int32),
-              ('planes', c_int32), ('reserved', c_int32)]
+              ('planes', c_int32), ('k_logical', c_int32)]
 
 
 class ResnetBlock(Structure):
@@ -96,6 +96,8 @@ SIGNATURES = {
     'tapir_last_error': (c_char_p, []),
     'tapir_abi_version': (ctypes.c_int, []),
     'tapir_launch_count': (c_ulonglong, []),
+    'tapir_profile_enable': (None, [c_int32]),
+    'tapir_profile_report': (ctypes.c_int, [ctypes.c_char_p, c_size_t]),
     'tapir_split_planes': (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64,
                                           c_int32, c_int32, c_int32, c_void_p]),
     'tapir_gemm': (ctypes.c_int, [c_void_p, c_int32, c_int64, POINTER(Linear), c_int64, c_int32,

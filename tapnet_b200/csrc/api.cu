@@ -3,6 +3,8 @@
 
 namespace tapir {
 const char* last_error();
+void profile_enable(int on);
+int profile_report(char* buf, size_t cap);
 }
 
 using namespace tapir;
@@ -16,6 +18,9 @@ extern "C" {
 const char* tapir_last_error(void) { return tapir::last_error(); }
 int tapir_abi_version(void) { return TAPIR_B200_ABI_VERSION; }
 unsigned long long tapir_launch_count(void) { return tapir::g_launch_count; }
+
+void tapir_profile_enable(int32_t on) { tapir::profile_enable(on); }
+int tapir_profile_report(char* buf, size_t capacity) { return tapir::profile_report(buf, capacity); }
 
 int tapir_split_planes(const float* src, int64_t ld_src, void* dst, int64_t ld_dst,
                        int64_t plane_stride, int64_t rows, int32_t cols, int32_t cols_padded,
@@ -46,6 +51,7 @@ int tapir_gemm(const void* a_planes, int32_t lda, int64_t a_plane_stride, const 
   g.ldb = b->K;
   g.b_plane_stride = (long long)b->N * b->K;
   g.bias = b->bias;
+  g.k_logical = b->k_logical;
   g.residual = residual; g.ldr = ldr;
   g.act = act_gelu ? 1 : 0;
   g.out_f32 = out_f32; g.ldo = ldo;

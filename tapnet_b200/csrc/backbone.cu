@@ -335,6 +335,7 @@ int split_planes(const float* src, long long ld_src, __nv_bfloat16* dst, long lo
                       ld_dst >= cols_padded && ld_src >= cols,
                   "split_planes: bad shape rows=%lld cols=%d padded=%d", rows, cols, cols_padded);
   const long long total = rows * cols_padded;
+  ProfileScope ps("split_planes", s, 0.0, (double)rows * cols * 4 + (double)total * 2 * planes);
   split_planes_kernel<<<grid_for(total), 256, 0, s>>>(src, ld_src, dst, ld_dst, plane_stride, rows,
                                                      cols, cols_padded, planes);
   count_launch();
@@ -351,6 +352,8 @@ int stem_conv(const float* video, const float* w_packed, int frames, int H, int 
     TAPIR_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
+  ProfileScope ps("backbone.stem_conv", s, 2.0 * frames * (H / 2) * (W / 2) * 64 * 147,
+                  (double)frames * H * W * 3 * 4 + (double)frames * (H / 2) * (W / 2) * 64 * 4);
   dim3 grid(ceil_div(W / 2, kStemTile), ceil_div(H / 2, kStemTile), frames);
   stem_conv_kernel<<<grid, 256, smem, s>>>(video, w_packed, H, W, out);
   count_launch();
@@ -361,6 +364,7 @@ int stem_conv(const float* video, const float* w_packed, int frames, int H, int 
 int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, float* mr,
                    cudaStream_t s) {
   TAPIR_CHECK_ARG(C == 64 || C == 128 || C == 256, "instnorm_stats: C=%d unsupported", C);
+  ProfileScope ps("backbone.instnorm_stats", s, 0.0, (double)frames * hw * C * 4);
   TAPIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * frames * C, s));
   dim3 grid((unsigned)ceil_div_ll(hw, kStatPixelsPerBlock), frames);
   instnorm_stats_kernel<<<grid, 256, 0, s>>>(x, hw, C, sums);
@@ -376,6 +380,7 @@ int instnorm_relu_split(const float* x, const float* mr, const float* w, const f
                         int frames, long long hw, int C, __nv_bfloat16* out, long long plane_stride,
                         int planes, cudaStream_t s) {
   const long long total4 = (long long)frames * hw * C / 4;
+  ProfileScope ps("backbone.instnorm_apply", s, 0.0, (double)total4 * (16 + 8 * planes));
   instnorm_relu_split_kernel<<<grid_for(total4), 256, 0, s>>>(x, mr, w, b, hw, C, out,
                                                              plane_stride, planes, total4);
   count_launch();
@@ -388,6 +393,7 @@ int im2col_s2(const __nv_bfloat16* in, long long in_plane_stride, int frames, in
   TAPIR_CHECK_ARG((taps == 1 || taps == 9) && C % 8 == 0 && H % 2 == 0 && W % 2 == 0,
                   "im2col_s2: bad arguments");
   const long long total8 = (long long)frames * (H / 2) * (W / 2) * taps * (C / 8);
+  ProfileScope ps("backbone.im2col", s, 0.0, (double)total8 * 32 * planes);
   im2col_s2_kernel<<<grid_for(total8), 256, 0, s>>>(in, in_plane_stride, H, W, C, taps, out,
                                                    out_plane_stride, planes, total8);
   count_launch();
@@ -398,6 +404,7 @@ int im2col_s2(const __nv_bfloat16* in, long long in_plane_stride, int frames, in
 int layernorm_split(const float* x, long long rows, int C, const float* w, const float* b,
                     float* y, __nv_bfloat16* planes_out, long long plane_stride, int planes,
                     cudaStream_t s) {
+  ProfileScope ps("layernorm", s, 0.0, (double)rows * C * (4 + (y ? 4 : 0) + (planes_out ? 2 * planes : 0)));
   const unsigned grid = (unsigned)ceil_div_ll(rows, 8);
   if (C == 256) {
     layernorm_split_kernel<256><<<grid, 256, 0, s>>>(x, rows, w, b, y, planes_out, plane_stride, planes);
@@ -413,6 +420,7 @@ int layernorm_split(const float* x, long long rows, int C, const float* w, const
 }
 
 int l2_normalize(const float* x, long long rows, int C, float* out, cudaStream_t s) {
+  ProfileScope ps("l2norm", s, 0.0, (double)rows * C * 8);
   const unsigned grid = (unsigned)ceil_div_ll(rows, 8);
   if (C == 128) {
     l2norm_kernel<128><<<grid, 256, 0, s>>>(x, rows, out);
@@ -430,6 +438,7 @@ int l2_normalize(const float* x, long long rows, int C, float* out, cudaStream_t
 int bilinear_resize(const float* src, int frames, int H, int W, int C, float* dst, int oH, int oW,
                     cudaStream_t s) {
   const long long total = (long long)frames * oH * oW * C;
+  ProfileScope ps("resize", s, 0.0, (double)total * 8);
   bilinear_resize_kernel<<<grid_for(total), 256, 0, s>>>(src, H, W, C, dst, oH, oW, total);
   count_launch();
   TAPIR_LAUNCH_CHECK("bilinear_resize_kernel");
@@ -475,6 +484,7 @@ GemmArgs linear_args(const tapir_linear& l) {
   g.ldb = l.K;
   g.b_plane_stride = (long long)l.N * l.K;
   g.bias = l.bias;
+  g.k_logical = l.k_logical;
   return g;
 }
 
@@ -521,6 +531,7 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
     const float* shortcut = x;
     if (b.has_proj) {
       GemmArgs g = linear_args(b.proj);
+      g.tag = "backbone.proj";
       g.M = (int)m_out;
       g.out_f32 = shortcut_buf;
       g.ldo = b.cout;
@@ -535,6 +546,7 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
     }
     {
       GemmArgs g = linear_args(b.conv0);
+      g.tag = "backbone.conv";
       g.M = (int)m_out;
       g.out_f32 = hbuf;
       g.ldo = b.cout;
@@ -553,6 +565,7 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
                                         b.cout, bp.act, bp.act_plane, P, s));
     {
       GemmArgs g = linear_args(b.conv1);
+      g.tag = "backbone.conv";
       g.mode = kGemmConv3x3;
       g.M = (int)m_out;
       g.a = bp.act; g.a_plane_stride = bp.act_plane;
@@ -578,6 +591,7 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
     TAPIR_RETURN_IF(layernorm_split(x, m, 256, b.ln_w, b.ln_b, y, bp.act, bp.act_plane, P, s));
     {
       GemmArgs g = linear_args(b.conv);
+      g.tag = "backbone.extra_conv";
       g.mode = kGemmConv3x3;
       g.M = (int)m;
       g.a = bp.act; g.a_plane_stride = bp.act_plane;
@@ -588,6 +602,7 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
     }
     {
       GemmArgs g = linear_args(b.conv1);
+      g.tag = "backbone.extra_conv";
       g.mode = kGemmConv3x3;
       g.M = (int)m;
       g.a = bp.col; g.a_plane_stride = bp.col_plane;

@@ -55,6 +55,17 @@ int num_sms();
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 
+// Optional per-launch device timing (tapir_profile_*): when enabled, a ProfileScope records a
+// CUDA event pair on the launch stream around one kernel launch and books the launch's
+// algorithmic FLOPs / bytes under `name`.  bench.py uses it for the roofline object.
+extern bool g_profile_on;
+struct ProfileScope {
+  int slot;
+  cudaStream_t stream;
+  ProfileScope(const char* name, cudaStream_t s, double flops, double bytes);
+  ~ProfileScope();
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

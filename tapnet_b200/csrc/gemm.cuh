@@ -42,6 +42,8 @@ struct GemmArgs {
   int ldp = 0;
   long long out_plane_stride = 0;
   int out_P = 0;
+  int k_logical = 0;        // un-padded K for FLOP accounting (0 = K)
+  const char* tag = nullptr;  // profiling class name
 };
 
 int validate_gemm_args(const GemmArgs& g);

@@ -111,6 +111,7 @@ int gemm_simt(const GemmArgs& g, cudaStream_t stream) {
     p.a_plane = g.a_plane_stride > 0 ? g.a_plane_stride : (long long)g.M * g.lda;
   }
   p.b_plane = g.b_plane_stride > 0 ? g.b_plane_stride : (long long)g.N * g.ldb;
+  ProfileScope ps(g.tag ? g.tag : "gemm", stream, 2.0 * g.M * g.N * (g.k_logical > 0 ? g.k_logical : g.K), 0.0);
   dim3 grid(ceil_div(g.M, TM), ceil_div(g.N, TN));
   gemm_simt_kernel<<<grid, 256, 0, stream>>>(p);
   count_launch();

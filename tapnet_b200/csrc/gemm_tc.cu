@@ -380,8 +380,13 @@ void choose_conv_tile(int H, int W, int* tw, int* th) {
 }
 
 template <int BLOCK_N, int P>
-int launch(const TcParams& p, cudaStream_t stream) {
+int launch(const TcParams& p, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_N, P>;
+  const double kl = g.k_logical > 0 ? g.k_logical : g.K;
+  const double out_b = (g.out_f32 ? 4.0 : 0.0) + (g.out_planes ? 2.0 * g.out_P : 0.0) + (g.residual ? 4.0 : 0.0);
+  const double a_elems = (g.mode == kGemmConv3x3) ? (double)g.M * g.C : (double)g.M * g.K;
+  ProfileScope ps(g.tag ? g.tag : "gemm", stream, 2.0 * g.M * g.N * kl,
+                  2.0 * P * (a_elems + (double)g.N * g.K) + out_b * g.M * g.N);
   static bool configured = false;
   if (!configured) {
     TAPIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, P>,
@@ -492,7 +497,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   }
 
 #define TAPIR_TC_CASE(BN, PP) \
-  if (bn == BN && P == PP) return launch<BN, PP>(p, stream);
+  if (bn == BN && P == PP) return launch<BN, PP>(p, g, stream);
   TAPIR_TC_CASE(64, 1) TAPIR_TC_CASE(64, 2) TAPIR_TC_CASE(64, 3)
   TAPIR_TC_CASE(128, 1) TAPIR_TC_CASE(128, 2) TAPIR_TC_CASE(128, 3)
   TAPIR_TC_CASE(256, 1) TAPIR_TC_CASE(256, 2)

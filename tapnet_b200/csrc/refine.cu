@@ -419,6 +419,7 @@ int grid_for(long long total, int block = 256) {
 int pool_pyramid(const float* grid, int T, int h, int w, int C, float* out, cudaStream_t s) {
   TAPIR_CHECK_ARG(grid && out && T > 0 && h >= 2 && w >= 2 && C % 4 == 0, "pool_pyramid: bad arguments");
   const long long total = (long long)T * (h / 2) * (w / 2) * (C / 4);
+  ProfileScope ps("pool_pyramid", s, 0.0, (double)total * 16 * 5);
   pool_kernel<<<grid_for(total), 256, 0, s>>>(reinterpret_cast<const float4*>(grid), h, w, C / 4,
                                              reinterpret_cast<float4*>(out), total);
   count_launch();
@@ -442,6 +443,11 @@ int local_corr(const tapir_corr_args* a, cudaStream_t s) {
   CorrParams p;
   p.a = *a;
   const long long rows = (long long)a->num_points * a->num_frames;
+  double cell_bytes = 0;
+  for (int l = 0; l < a->num_levels; ++l) cell_bytes += 64.0 * a->levels[l].C * 4;
+  // N*T*(64 cells * sum C * e + 384*4 + 8 + 147*4)
+  ProfileScope ps("local_corr", s, (double)rows * (cell_bytes / 2 + 1200),
+                  (double)rows * (cell_bytes + 384 * 4 + 8 + 49.0 * a->num_levels * 4));
   local_corr_kernel<<<(unsigned)rows, 96, 0, s>>>(p);
   count_launch();
   TAPIR_LAUNCH_CHECK("local_corr_kernel");
@@ -452,6 +458,7 @@ int refine_update(const tapir_update_args* a, cudaStream_t s) {
   TAPIR_CHECK_ARG(a != nullptr && a->res && a->pos && a->feat_out && a->occ_out && a->expd_out,
                   "refine_update: null pointer");
   const long long rows = (long long)a->num_points * a->num_frames;
+  ProfileScope ps("refine_update", s, 0.0, (double)rows * (388 * 4 + 384 * 8));
   refine_update_kernel<<<(unsigned)rows, 128, 0, s>>>(*a);
   count_launch();
   TAPIR_LAUNCH_CHECK("refine_update_kernel");
@@ -483,6 +490,7 @@ GemmArgs lin(const tapir_linear& l) {
   g.ldb = l.K;
   g.b_plane_stride = (long long)l.N * l.K;
   g.bias = l.bias;
+  g.k_logical = l.k_logical;
   return g;
 }
 }  // namespace
@@ -518,6 +526,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
   }
   {  // nets.py:235 linear
     GemmArgs g = lin(w->linear);
+    g.tag = "mixer.linear_in";
     g.M = (int)rows;
     g.a = static_cast<const __nv_bfloat16*>(io->x_planes);
     g.lda = io->ldx;
@@ -538,11 +547,13 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     d.ctx1_out = io->ctx1_out ? io->ctx1_out[b] : nullptr;
     d.ctx2_out = io->ctx2_out ? io->ctx2_out[b] : nullptr;
     dim3 grid(ceil_div(T, kDwTile), n);
+    ProfileScope ps("mixer.dw", s, (double)rows * 2048 * 12, (double)rows * 512 * (8 + 2 * P));
     mixer_dw_kernel<<<grid, 512, dw_smem, s>>>(d);
     count_launch();
     TAPIR_LAUNCH_CHECK("mixer_dw_kernel");
     {
       GemmArgs g = lin(blk.up);
+      g.tag = "mixer.up";
       g.M = (int)rows;
       g.a = m.y; g.lda = 512; g.a_plane_stride = rows * 512;
       g.act = 1;
@@ -551,6 +562,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     }
     {
       GemmArgs g = lin(blk.down);
+      g.tag = "mixer.down";
       g.M = (int)rows;
       g.a = m.h; g.lda = 2048; g.a_plane_stride = rows * 2048;
       g.residual = m.xb; g.ldr = 512;
@@ -561,6 +573,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
   TAPIR_RETURN_IF(layernorm_split(m.xa, rows, 512, w->ln_w, nullptr, nullptr, m.y, rows * 512, P, s));
   {
     GemmArgs g = lin(w->linear_1);
+    g.tag = "mixer.linear_out";
     g.M = (int)rows;
     g.a = m.y; g.lda = 512; g.a_plane_stride = rows * 512;
     g.out_f32 = io->out; g.ldo = io->ldo;

@@ -308,6 +308,7 @@ int sample_query_features(const float* grid, int T, int gh, int gw, int C, const
                           int N, int vT, int vH, int vW, float* out, cudaStream_t s) {
   TAPIR_CHECK_ARG(grid && query_tyx && out && N > 0 && T > 0 && gh > 0 && gw > 0 && C > 0,
                   "sample_query_features: bad arguments");
+  ProfileScope ps("sample_query", s, 0.0, (double)N * C * 4 * 9);
   sample_query_kernel<<<N, 128, 0, s>>>(grid, T, gh, gw, C, query_tyx, vT, vH, vW, out);
   count_launch();
   TAPIR_LAUNCH_CHECK("sample_query_kernel");
@@ -324,6 +325,8 @@ int cost_volume_head(const tapir_head_weights* w, const float* cost_volume, int 
     configured = true;
   }
   TAPIR_CHECK_ARG(N <= 65535, "cost_volume_head: at most 65535 queries per call (got %d)", N);
+  // head = 2,950,208 FLOP per (n,t); 4 KB map in, 16 B out
+  ProfileScope ps("cost_volume.head", s, 2950208.0 * N * T, (double)N * T * (4096 + 16));
   dim3 grid(T, N);
   cost_volume_head_kernel<<<grid, 256, sizeof(HeadSmem), s>>>(*w, cost_volume, T, query_tyx, temperature,
                                                              init_h, init_w, points, occ, expd, argmax);
@@ -384,6 +387,7 @@ int cost_volume_tracks(const tapir_head_weights* w, const float* qfeat, const fl
   g.a = p.q; g.lda = C; g.a_plane_stride = (long long)N * C;
   g.b = p.g; g.ldb = C; g.b_plane_stride = cells * C;
   g.out_f32 = p.cv; g.ldo = (int)cells;
+  g.tag = "cost_volume.gemm";
   TAPIR_RETURN_IF(gemm(g, s));
   return cost_volume_head(w, p.cv, N, T, query_tyx, temperature, init_h, init_w, points, occ, expd,
                           argmax, s);

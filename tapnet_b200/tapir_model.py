@@ -210,7 +210,7 @@ class TAPIR(nn.Module):
                                         stream), 'tapir_split_planes')
       b = f32(bias) if bias is not None else None
       return _lib.Linear(w=dst.data_ptr(), bias=(b.data_ptr() if b is not None else None), N=n,
-                         K=kp, planes=planes, reserved=0)
+                         K=kp, planes=planes, k_logical=k)
 
     def conv(wkey, bkey=None):
       w = sd[wkey]

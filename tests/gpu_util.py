@@ -74,7 +74,7 @@ def planes_matmul_fp64(a_pl, b_pl):
 def make_linear(w_pl, bias):
   P, n, k = w_pl.shape
   return _lib.Linear(w=w_pl.data_ptr(), bias=(bias.data_ptr() if bias is not None else None), N=n,
-                     K=k, planes=P, reserved=0)
+                     K=k, planes=P, k_logical=k)
 
 
 def gemm(a_pl, w_pl, bias=None, residual=None, gelu=False, out_f32=True, out_planes=0, impl=0,
