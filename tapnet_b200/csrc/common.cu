@@ -37,6 +37,21 @@ struct ProfRec {
 };
 std::vector<ProfRec> g_recs;
 std::vector<std::string> g_names;
+std::vector<cudaEvent_t> g_event_pool;  // events are recycled: creating them in the launch
+                                        // path starves the GPU and inflates the timings
+bool take_event(cudaEvent_t* e) {
+  if (g_event_pool.empty()) {
+    for (int i = 0; i < 1024; ++i) {
+      cudaEvent_t ev;
+      if (cudaEventCreate(&ev) != cudaSuccess) break;
+      g_event_pool.push_back(ev);
+    }
+    if (g_event_pool.empty()) return false;
+  }
+  *e = g_event_pool.back();
+  g_event_pool.pop_back();
+  return true;
+}
 int name_id(const char* n) {
   for (size_t i = 0; i < g_names.size(); ++i)
     if (g_names[i] == n) return (int)i;
@@ -49,7 +64,7 @@ ProfileScope::ProfileScope(const char* name, cudaStream_t s, double flops, doubl
     : slot(-1), stream(s) {
   if (!g_profile_on) return;
   ProfRec r;
-  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  if (!take_event(&r.a) || !take_event(&r.b)) return;
   r.name_id = name_id(name);
   r.flops = flops;
   r.bytes = bytes;
@@ -61,7 +76,16 @@ ProfileScope::~ProfileScope() {
   if (slot >= 0) cudaEventRecord(g_recs[slot].b, stream);
 }
 
-void profile_enable(int on) { g_profile_on = on != 0; }
+void profile_enable(int on) {
+  g_profile_on = on != 0;
+  if (g_profile_on && g_event_pool.size() < 2048) {  // pre-create outside the timed launches
+    for (int i = 0; i < 2048; ++i) {
+      cudaEvent_t ev;
+      if (cudaEventCreate(&ev) != cudaSuccess) break;
+      g_event_pool.push_back(ev);
+    }
+  }
+}
 
 // Synchronises, aggregates per name and clears.  JSON: {"name": {"launches":n,"ms":t,
 // "flops":f,"bytes":b}, ...}
@@ -75,8 +99,8 @@ int profile_report(char* buf, size_t cap) {
       Agg& a = agg[r.name_id];
       a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
     }
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
+    g_event_pool.push_back(r.a);
+    g_event_pool.push_back(r.b);
   }
   g_recs.clear();
   std::string out = "{";

@@ -1,11 +1,11 @@
 // tcgen05 / TMEM / TMA split-bf16 GEMM and implicit-GEMM 3x3 convolution for sm_100a.
 //
-// One persistent CTA per SM, 6 warps:
+// One persistent CTA per SM, 10 warps:
 //   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor tiles of A and B planes into a
 //                      multi-stage shared-memory ring (128B-swizzled, K-major)
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16,
 //                      fp32 accumulators in TMEM (double buffered: 2 x BLOCK_N columns)
-//   warps 2..5         epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row
+//   warps 2..9         epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row
 //                      per thread), bias / tanh-GELU / residual, store fp32 and/or bf16 planes
 // Pipelines: full/empty mbarriers between TMA and MMA, tmem_full/tmem_empty between MMA and
 // epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -29,7 +29,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
+constexpr int kNumEpilogueWarps = 8;
+constexpr int kThreads = 64 + 32 * kNumEpilogueWarps;
 constexpr int kNumAccStages = 2;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarrierBytes = 256;
@@ -175,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     }
     for (int a = 0; a < kNumAccStages; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[a], kNumEpilogueWarps);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tmA);
@@ -272,7 +273,12 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    // 8 warps: TMEM lane quadrant q = warp % 4 (hardware restriction: a warp may only touch
+    // lanes [32*(warp%4), +32)), column half = (warp - 2) / 4.  TMEM loads are software
+    // pipelined: chunk i+1 is in flight while chunk i goes through bias / GELU / stores.
+    constexpr int kChunks = BLOCK_N / 64;  // 32-column chunks per warp
+    const int q = warp & 3;
+    const int cbase = ((warp - 2) >> 2) * kChunks;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -296,14 +302,26 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
       }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 104);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
-        ptx::tmem_ld_wait();
-        if (row_ok) store_row_chunk(p, row, col0, v);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + cbase * 32;
+      const int colbase = n0 + cbase * 32;
+      uint32_t va[32], vb[32];
+      if (colbase < p.N) ptx::tmem_ld_32x32(taddr, va);  // all conditions are warp-uniform
+#pragma unroll
+      for (int i = 0; i < kChunks; i += 2) {
+        const int col0 = colbase + i * 32;
+        if (col0 < p.N) {
+          ptx::tmem_ld_wait();
+          if (i + 1 < kChunks && col0 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 1) * 32, vb);
+          if (row_ok) store_row_chunk(p, row, col0, va);
+        }
+        if (i + 1 < kChunks) {
+          const int col1 = col0 + 32;
+          if (col1 < p.N) {
+            ptx::tmem_ld_wait();
+            if (i + 2 < kChunks && col1 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 2) * 32, va);
+            if (row_ok) store_row_chunk(p, row, col1, vb);
+          }
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
