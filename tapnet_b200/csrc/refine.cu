@@ -547,8 +547,10 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     d.ctx1_out = io->ctx1_out ? io->ctx1_out[b] : nullptr;
     d.ctx2_out = io->ctx2_out ? io->ctx2_out[b] : nullptr;
     dim3 grid(ceil_div(T, kDwTile), n);
-    ProfileScope ps("mixer.dw", s, (double)rows * 2048 * 12, (double)rows * 512 * (8 + 2 * P));
-    mixer_dw_kernel<<<grid, 512, dw_smem, s>>>(d);
+    {
+      ProfileScope ps("mixer.dw", s, (double)rows * 2048 * 12, (double)rows * 512 * (8 + 2 * P));
+      mixer_dw_kernel<<<grid, 512, dw_smem, s>>>(d);
+    }
     count_launch();
     TAPIR_LAUNCH_CHECK("mixer_dw_kernel");
     {

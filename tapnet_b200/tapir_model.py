@@ -320,13 +320,16 @@ class TAPIR(nn.Module):
   ) -> FeatureGrids:
     """Reference tapir_model.py:293-392.  video: [B, T, H, W, 3] float in [-1, 1]."""
     del is_training
-    dev = self._device_check(video)
-    lib = _lib.load()
-    pk = self._pack()
     if refinement_resolutions is None:
       refinement_resolutions = generate_default_resolutions(video.shape[2:4],
                                                             self.initial_resolution)
     all_required = [tuple(self.initial_resolution)] + [tuple(r) for r in refinement_resolutions]
+    for resolution in all_required:
+      if resolution[0] % 8 != 0 or resolution[1] % 8 != 0:
+        raise ValueError('Image resolution must be a multiple of 8.')
+    dev = self._device_check(video)
+    lib = _lib.load()
+    pk = self._pack()
     video = video.to(torch.float32).contiguous()
     n, f, vh, vw, _ = video.shape
     feature_grid, hires_feats, resize_im_shape = [], [], []

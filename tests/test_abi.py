@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every symbol include/tapir_b200.h declares (no GPU)."""
+import ctypes
+import os
+import re
+
+from tapnet_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+  with open(os.path.join(ROOT, 'include', 'tapir_b200.h')) as fh:
+    src = fh.read()
+  src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+  names = re.findall(r'\b(tapir_[a-z0-9_]+)\s*\(', src)
+  return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+  lib = _lib.load()
+  declared = _declared_functions()
+  assert len(declared) >= 17
+  for name in declared:
+    assert hasattr(lib, name), f'{name} declared in the header but not exported'
+  # and the ctypes table binds exactly the declared set
+  assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_version_and_error_string():
+  lib = _lib.load()
+  assert lib.tapir_abi_version() == 1
+  assert isinstance(lib.tapir_last_error(), bytes)
+
+
+def test_workspace_queries_need_no_gpu():
+  lib = _lib.load()
+  assert lib.tapir_backbone_workspace_bytes(48, 256, 256, 1, 2) > 1 << 30
+  assert lib.tapir_mixer_workspace_bytes(12288, 2) == 12288 * (512 * 4 * 2 + 512 * 2 * 2 + 2048 * 2 * 2) + 256
+  assert lib.tapir_cost_volume_workspace_bytes(256, 48, 32, 32, 256) > 256 * 48 * 1024 * 4
+
+
+def test_struct_sizes_match_header():
+  # computed from the C declarations (LP64): guards the ctypes mirror against drift
+  assert ctypes.sizeof(_lib.Linear) == 32
+  assert ctypes.sizeof(_lib.ResnetBlock) == 3 * 32 + 4 * 8 + 16
+  assert ctypes.sizeof(_lib.ExtraBlock) == 16 + 64
+  assert ctypes.sizeof(_lib.BackboneWeights) == 8 + 8 * 144 + 5 * 80 + 8
+  assert ctypes.sizeof(_lib.HeadWeights) == 80
+  assert ctypes.sizeof(_lib.MixerBlock) == 48 + 64
+  assert ctypes.sizeof(_lib.MixerWeights) == 64 + 8 + 12 * 112 + 8
+  assert ctypes.sizeof(_lib.MixerIO) == 8 + 8 + 16 + 32 + 8 + 8
+  assert ctypes.sizeof(_lib.CorrArgs) == 72 + 24 + 24 + 48 + 24
+  assert ctypes.sizeof(_lib.UpdateArgs) == 8 + 40 + 48 + 7 * 8

@@ -1,0 +1,68 @@
+"""Host-side mirror of the reference interface (CPU only: no compute calls)."""
+import pytest
+import torch
+
+from oracle import synth
+from tapnet_b200 import schema, tapir_model
+
+
+def test_state_dict_layout_and_load():
+  m = tapir_model.TAPIR(pyramid_level=1)
+  sd = m.state_dict()
+  assert list(sd.keys()) == list(schema.state_dict_schema().keys())
+  m.load_state_dict(synth.make_state_dict(0))  # strict load of a reference-layout dict
+  m0 = tapir_model.TAPIR(pyramid_level=0, extra_convs=False)
+  assert len(m0.state_dict()) == 188 and m0.extra_convs is None
+
+
+def test_ctor_surface_matches_reference_keywords():
+  m = tapir_model.TAPIR(bilinear_interp_with_depthwise_conv=False, num_pips_iter=4, pyramid_level=1,
+                        mixer_hidden_dim=512, num_mixer_blocks=12, mixer_kernel_shape=3,
+                        patch_size=7, softmax_temperature=20.0,
+                        parallelize_query_extraction=False, initial_resolution=(256, 256),
+                        blocks_per_group=(2, 2, 2, 2), feature_extractor_chunk_size=10,
+                        extra_convs=True, use_casual_conv=True)
+  assert m.use_casual_conv and m.initial_resolution == (256, 256)
+  for name in ('forward', 'get_feature_grids', 'get_query_features', 'estimate_trajectories',
+               'construct_initial_causal_state', 'update_query_features'):
+    assert callable(getattr(m, name))
+
+
+def test_errors_match_reference():
+  m = tapir_model.TAPIR()
+  with pytest.raises(ValueError, match='Get query feats not supported in TAPIR.'):
+    m(torch.zeros(1, 2, 256, 256, 3), torch.zeros(1, 4, 3), get_query_feats=True)
+  with pytest.raises(ValueError, match='multiple of 8'):
+    m.get_feature_grids(torch.zeros(1, 1, 256, 256, 3), False, refinement_resolutions=[(250, 256)])
+  with pytest.raises(RuntimeError, match='CUDA only'):
+    m(torch.zeros(1, 2, 256, 256, 3), torch.zeros(1, 4, 3))
+
+
+def test_causal_state_shape_and_aliasing():
+  m = tapir_model.TAPIR(use_casual_conv=True)
+  st = m.construct_initial_causal_state(5, 2)
+  assert len(st) == 8 and st[0] is st[7]  # reference returns the same dict 4*L times
+  assert st[0]['block_11_causal_2'].shape == (1, 5, 2, 2048)
+  assert sorted(st[0])[0] == 'block_0_causal_1' and len(st[0]) == 24
+
+
+def test_update_query_features_in_place():
+  m = tapir_model.TAPIR(use_casual_conv=True)
+  lo, hi = torch.zeros(1, 4, 256), torch.zeros(1, 4, 128)
+  qf = tapir_model.QueryFeatures((lo, lo), (hi, hi), ((256, 256), (256, 256)))
+  new = tapir_model.QueryFeatures((torch.ones(1, 1, 256),) * 2, (torch.ones(1, 1, 128),) * 2,
+                                  ((256, 256), (256, 256)))
+  st = m.construct_initial_causal_state(4, 1)
+  for d in st:
+    for v in d.values():
+      v.fill_(3.0)
+  qf2, st2 = m.update_query_features(qf, new, 2, st)
+  assert lo[0, 2].eq(1).all() and lo[0, 1].eq(0).all() and qf2.lowres[0] is lo
+  assert st2[0]['block_0_causal_1'][0, 2].eq(0).all() and st2[0]['block_0_causal_1'][0, 1].eq(3).all()
+
+
+def test_default_resolutions():
+  f = tapir_model.generate_default_resolutions
+  assert f((256, 256), (256, 256)) == [(256, 256)]
+  assert f((480, 480), (256, 256)) == [(256, 256), (480, 480)]
+  assert f((1024, 1024), (256, 256)) == [(256, 256), (512, 512), (1024, 1024)]
