@@ -162,15 +162,9 @@ __global__ void __launch_bounds__(256) instnorm_relu_split_kernel(
       y[e] = fmaxf(t, 0.f);
     }
     for (int q = 0; q < planes; ++q) {
-      __nv_bfloat16 h[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        h[e] = __float2bfloat16_rn(y[e]);
-        y[e] -= __bfloat162float(h[e]);
-      }
       uint2 pk;
-      pk.x = pack_bf16x2(h[0], h[1]);
-      pk.y = pack_bf16x2(h[2], h[3]);
+      pk.x = bf16x2_split(y[0], y[1]);
+      pk.y = bf16x2_split(y[2], y[3]);
       reinterpret_cast<uint2*>(out + q * plane_stride)[i] = pk;
     }
   }
@@ -250,15 +244,9 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(
     if (y != nullptr) *reinterpret_cast<float4*>(y + row * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
     if (pl != nullptr) {
       for (int q = 0; q < planes; ++q) {
-        __nv_bfloat16 h[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          h[e] = __float2bfloat16_rn(o[e]);
-          o[e] -= __bfloat162float(h[e]);
-        }
         uint2 pk;
-        pk.x = pack_bf16x2(h[0], h[1]);
-        pk.y = pack_bf16x2(h[2], h[3]);
+        pk.x = bf16x2_split(o[0], o[1]);
+        pk.y = bf16x2_split(o[2], o[3]);
         *reinterpret_cast<uint2*>(pl + q * plane_stride + row * C + c0) = pk;
       }
     }

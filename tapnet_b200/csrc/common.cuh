@@ -90,10 +90,24 @@ __device__ __forceinline__ float warp_max(float v) {
 //   0.5 x (1 + tanh(k (x + 0.044715 x^3))) == x * sigmoid(2 k (x + 0.044715 x^3))
 // evaluated through ex2.approx (|rel err| ~1e-6, far inside the 1e-4 logit budget).
 __device__ __forceinline__ float gelu_tanh(float x) {
-  const float k2 = 1.5957691216057308f;  // 2*sqrt(2/pi)
-  float u = k2 * (x + 0.044715f * x * x * x);
-  float e = __expf(-u);
+  // e = exp(-2k(x + c x^3)) = 2^(x * (A + B x^2)),  A = -2k log2(e),  B = A * 0.044715
+  const float A = -2.3022081983f;
+  const float B = -0.1029432396f;
+  const float u = x * fmaf(x * x, B, A);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u));
   return __fdividef(x, 1.0f + e);
+}
+
+// One step of the bf16 split for two values at once: returns bf16x2(a, b) (a in the low half)
+// and replaces a, b by their residuals.  Uses the packed convert (F2FP, full rate) instead of
+// two scalar F2F conversions (quarter-rate unit, scoreboard latency).
+__device__ __forceinline__ uint32_t bf16x2_split(float& a, float& b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+  a -= __uint_as_float(u << 16);
+  b -= __uint_as_float(u & 0xffff0000u);
+  return u;
 }
 
 // Split an fp32 value into P bf16 terms: x ~= p0 + p1 (+ p2); each term is the bf16

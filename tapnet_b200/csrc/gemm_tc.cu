@@ -61,33 +61,31 @@ struct TcCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = P * (kABytes + kBBytes);
-  static constexpr int kAvail = kSmemLimit - 1024 - kBarrierBytes;
+  static constexpr int kBiasBytes = kNumEpilogueWarps * (BLOCK_N / 2) * 4;  // per-warp bias slice
+  static constexpr int kAvail = kSmemLimit - 1024 - kBarrierBytes - kBiasBytes;
   static constexpr int kStagesRaw = kAvail / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarrierBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarrierBytes + kBiasBytes;
   static constexpr int kTmemCols = (kNumAccStages * BLOCK_N <= 128) ? 128
                                    : (kNumAccStages * BLOCK_N <= 256) ? 256 : 512;
   static_assert(kStages >= 1, "tile does not fit in shared memory");
   static_assert(kStages * 2 + 2 * kNumAccStages <= (kBarrierBytes - 16) / 8, "barrier space");
 };
 
+// One output row (this thread) x 32 consecutive columns.  `bias_s` points at this chunk's 32
+// bias values in shared memory (staged by the warp before it waited for the accumulator).
 __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row, int col0,
-                                                const uint32_t (&acc)[32]) {
+                                                const uint32_t (&acc)[32],
+                                                const float* __restrict__ bias_s) {
   const bool full = (col0 + 32 <= p.N);
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   if (p.bias != nullptr) {
-    if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + j);  // broadcast LDS.128
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
   if (p.act == 1) {
@@ -127,17 +125,11 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
       if (full && (p.ldp & 7) == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          __nv_bfloat16 h[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            h[t] = __float2bfloat16_rn(v[j + t]);
-            v[j + t] -= __bfloat162float(h[t]);
-          }
           uint4 w;
-          w.x = pack_bf16x2(h[0], h[1]);
-          w.y = pack_bf16x2(h[2], h[3]);
-          w.z = pack_bf16x2(h[4], h[5]);
-          w.w = pack_bf16x2(h[6], h[7]);
+          w.x = bf16x2_split(v[j], v[j + 1]);
+          w.y = bf16x2_split(v[j + 2], v[j + 3]);
+          w.z = bf16x2_split(v[j + 4], v[j + 5]);
+          w.w = bf16x2_split(v[j + 6], v[j + 7]);
           *reinterpret_cast<uint4*>(o + j) = w;
         }
       } else {
@@ -165,6 +157,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + kNumAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kNumAccStages);
+  float* bias_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + kBarrierBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -279,6 +272,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int kChunks = BLOCK_N / 64;  // 32-column chunks per warp
     const int q = warp & 3;
     const int cbase = ((warp - 2) >> 2) * kChunks;
+    float* bias_w = bias_smem + (warp - 2) * (kChunks * 32);  // private to this warp
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -300,10 +294,19 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
         row = (long long)m_tile * kBlockM + r;
         row_ok = row < p.M;
       }
+      const int colbase = n0 + cbase * 32;
+      if (p.bias != nullptr) {  // stage this warp's bias slice while the main loop runs
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kChunks; ++j) {
+          const int c = colbase + j * 32 + lane;
+          bias_w[j * 32 + lane] = (c < p.N) ? __ldg(p.bias + c) : 0.f;
+        }
+        __syncwarp();
+      }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 104);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + cbase * 32;
-      const int colbase = n0 + cbase * 32;
       uint32_t va[32], vb[32];
       if (colbase < p.N) ptx::tmem_ld_32x32(taddr, va);  // all conditions are warp-uniform
 #pragma unroll
@@ -312,14 +315,14 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (col0 < p.N) {
           ptx::tmem_ld_wait();
           if (i + 1 < kChunks && col0 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 1) * 32, vb);
-          if (row_ok) store_row_chunk(p, row, col0, va);
+          if (row_ok) store_row_chunk(p, row, col0, va, bias_w + i * 32);
         }
         if (i + 1 < kChunks) {
           const int col1 = col0 + 32;
           if (col1 < p.N) {
             ptx::tmem_ld_wait();
             if (i + 2 < kChunks && col1 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 2) * 32, va);
-            if (row_ok) store_row_chunk(p, row, col1, vb);
+            if (row_ok) store_row_chunk(p, row, col1, vb, bias_w + (i + 1) * 32);
           }
         }
       }

@@ -159,20 +159,19 @@ __global__ void __launch_bounds__(96) local_corr_kernel(const CorrParams p) {
   const int ncorr = 49 * a.num_levels;
   const float occ = a.occ[row], expd = a.expd[row];
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a.out_planes);
-  for (int e = threadIdx.x; e < a.ld; e += blockDim.x) {
-    float v;
-    if (e < 2) v = 0.f;  // position slots are zeroed (tapir_model.py:647)
-    else if (e == 2) v = occ;
-    else if (e == 3) v = expd;
-    else if (e < 4 + 128) v = fhi[e - 4];
-    else if (e < 4 + 384) v = flo[e - 132];
-    else if (e < 388 + ncorr) v = corr[e - 388];
-    else v = 0.f;
-    for (int q = 0; q < a.planes; ++q) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      v -= __bfloat162float(h);
-      out[q * a.out_plane_stride + row * a.ld + e] = h;
-    }
+  auto value = [&](int e) -> float {
+    if (e < 2) return 0.f;  // position slots are zeroed (tapir_model.py:647)
+    if (e == 2) return occ;
+    if (e == 3) return expd;
+    if (e < 4 + 128) return fhi[e - 4];
+    if (e < 4 + 384) return flo[e - 132];
+    if (e < 388 + ncorr) return corr[e - 388];
+    return 0.f;
+  };
+  for (int e2 = threadIdx.x; e2 < a.ld / 2; e2 += blockDim.x) {
+    float v0 = value(2 * e2), v1 = value(2 * e2 + 1);
+    for (int q = 0; q < a.planes; ++q)
+      *reinterpret_cast<uint32_t*>(out + q * a.out_plane_stride + row * a.ld + 2 * e2) = bf16x2_split(v0, v1);
   }
 }
 
@@ -210,7 +209,7 @@ struct DwParams {
   float* ctx2_out;
 };
 
-__global__ void __launch_bounds__(512) mixer_dw_kernel(const DwParams p) {
+__global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
   extern __shared__ float dw_smem[];  // [kDwRows][512] LN'd rows, later reused for z
   const int n = blockIdx.y;
   const int t0 = blockIdx.x * kDwTile;
@@ -290,31 +289,8 @@ __global__ void __launch_bounds__(512) mixer_dw_kernel(const DwParams p) {
     }
   };
 
-  float ha[4], hb[4], hc[4];  // sliding window of h1 over 3 consecutive frames
-  const int first = p.causal ? t0 - 2 : t0 - 1;
-  h1(first, ha);
-  h1(first + 1, hb);
-  float zreg[kDwTile];
-#pragma unroll
-  for (int i = 0; i < kDwTile; ++i) {
-    const int t = t0 + i;
-    if (t < t1) {
-      h1(first + 2 + i, hc);
-      float acc = xn[(long long)t * 512 + c];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        acc += fmaf(w2[j][2], hc[j], fmaf(w2[j][1], hb[j], fmaf(w2[j][0], ha[j], b2[j])));
-      zreg[i] = acc;
-      // new causal context (last two frames of [ctx | y] and [ctx | h1], nets.py:153,167)
-      if (p.causal && p.ctx2_out != nullptr && t >= p.T - 2) {
-        // frame t's own h1 is hc (causal window = frames t-2, t-1, t)
-        *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + (t - (p.T - 2))) * 2048 + 4 * c) =
-            make_float4(hc[0], hc[1], hc[2], hc[3]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { ha[j] = hb[j]; hb[j] = hc[j]; }
-    }
-  }
+  // new causal context for the layer-normed input: last two frames of [ctx | y]
+  // (nets.py:153).  Written first: the y rows are recycled for z below.
   if (p.causal && p.ctx1_out != nullptr) {
     for (int t = max(t0, p.T - 2); t < t1; ++t) p.ctx1_out[((long long)n * 2 + (t - (p.T - 2))) * 512 + c] = yv(t);
     if (p.T == 1 && t0 == 0) {
@@ -327,14 +303,30 @@ __global__ void __launch_bounds__(512) mixer_dw_kernel(const DwParams p) {
       }
     }
   }
-  __syncthreads();  // everyone is done reading y from smem
-#pragma unroll
-  for (int i = 0; i < kDwTile; ++i) {
+  float ha[4], hb[4], hc[4];  // sliding window of h1 over 3 consecutive frames
+  const int first = p.causal ? t0 - 2 : t0 - 1;
+  h1(first, ha);
+  h1(first + 1, hb);
+  // Column c of the y rows is only ever read by this thread, and after step i the rows
+  // <= i + 2 are dead (both modes), so z[t0 + i] is parked in row i: no per-thread z array.
+#pragma unroll 2
+  for (int i = 0; i < t1 - t0; ++i) {
     const int t = t0 + i;
-    if (t < t1) {
-      dw_smem[i * 512 + c] = zreg[i];
-      p.z[((long long)n * p.T + t) * 512 + c] = zreg[i];
+    h1(first + 2 + i, hc);
+    float acc = xn[(long long)t * 512 + c];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      acc += fmaf(w2[j][2], hc[j], fmaf(w2[j][1], hb[j], fmaf(w2[j][0], ha[j], b2[j])));
+    dw_smem[i * 512 + c] = acc;
+    p.z[((long long)n * p.T + t) * 512 + c] = acc;
+    // new causal context of the hidden activation (last two frames of [ctx | h1], nets.py:167)
+    if (p.causal && p.ctx2_out != nullptr && t >= p.T - 2) {
+      // frame t's own h1 is hc (causal window = frames t-2, t-1, t)
+      *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + (t - (p.T - 2))) * 2048 + 4 * c) =
+          make_float4(hc[0], hc[1], hc[2], hc[3]);
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ha[j] = hb[j]; hb[j] = hc[j]; }
   }
   __syncthreads();
   // LN_1 (scale only) -> bf16 planes
@@ -362,15 +354,9 @@ __global__ void __launch_bounds__(512) mixer_dw_kernel(const DwParams p) {
       float o[4] = {(v[i].x - mean) * rstd * ww.x, (v[i].y - mean) * rstd * ww.y,
                     (v[i].z - mean) * rstd * ww.z, (v[i].w - mean) * rstd * ww.w};
       for (int q = 0; q < p.planes; ++q) {
-        __nv_bfloat16 h[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          h[e] = __float2bfloat16_rn(o[e]);
-          o[e] -= __bfloat162float(h[e]);
-        }
         uint2 pk;
-        pk.x = pack_bf16x2(h[0], h[1]);
-        pk.y = pack_bf16x2(h[2], h[3]);
+        pk.x = bf16x2_split(o[0], o[1]);
+        pk.y = bf16x2_split(o[2], o[3]);
         *reinterpret_cast<uint2*>(p.planes_out + q * p.plane_stride + orow * 512 + (i * 32 + lane) * 4) = pk;
       }
     }
