@@ -25,6 +25,7 @@ for t in $TIERS; do
     stages_tc)   run stages_tc "X=1" tests/test_stages_gpu.py ;;
     e2e_simt)    run e2e_simt "TAPIR_B200_GEMM=simt" tests/test_end_to_end_gpu.py ;;
     e2e_tc)      run e2e_tc "X=1" tests/test_end_to_end_gpu.py ;;
+    props)       run props "X=1" tests/test_properties_gpu.py ;;
     all)         run all "X=1" tests ;;
   esac
 done
