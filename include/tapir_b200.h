@@ -194,12 +194,14 @@ int tapir_split_planes(const float* src, int64_t ld_src, void* dst, int64_t ld_d
 
 /* Generic split-bf16 GEMM  out = act(A . B^T + bias) + residual  (see csrc/gemm.cuh).
  * impl: 0 = tcgen05 (product path), 1 = SIMT cross-check. conv3x3 != 0 treats A as NHWC
- * planes [planes][frames][H][W][C] (stride 1, zero padding 1). */
+ * planes [planes][frames][H][W][C] (stride 1, zero padding 1).  stats (nullable): fp64
+ * [frames][N][2] accumulators that receive the per-(frame, column) sum and sum of squares of
+ * the output (the InstanceNorm statistics of the produced tensor); the caller zeroes them. */
 int tapir_gemm(const void* a_planes, int32_t lda, int64_t a_plane_stride, const tapir_linear* b,
                int64_t M, int32_t conv3x3, int32_t frames, int32_t H, int32_t W, int32_t C,
                const float* residual, int32_t ldr, int32_t act_gelu, float* out_f32, int32_t ldo,
                void* out_planes, int32_t ldp, int64_t out_plane_stride, int32_t out_P,
-               int32_t impl, void* stream);
+               double* stats, int32_t rows_per_frame, int32_t impl, void* stream);
 
 /* ---- a3: tapir_model.py:293-392 get_feature_grids (one resolution, one frame chunk) ---- */
 /* utils.py:26-42 bilinear resize, align_corners=False, [frames][H][W][C] -> [frames][oH][oW][C] */

@@ -34,7 +34,7 @@ int tapir_gemm(const void* a_planes, int32_t lda, int64_t a_plane_stride, const 
                int64_t M, int32_t conv3x3, int32_t frames, int32_t H, int32_t W, int32_t C,
                const float* residual, int32_t ldr, int32_t act_gelu, float* out_f32, int32_t ldo,
                void* out_planes, int32_t ldp, int64_t out_plane_stride, int32_t out_P,
-               int32_t impl, void* stream) {
+               double* stats, int32_t rows_per_frame, int32_t impl, void* stream) {
   TAPIR_CHECK_ARG(a_planes != nullptr && b != nullptr && b->w != nullptr, "tapir_gemm: null pointer");
   TAPIR_CHECK_ARG(M > 0 && M < (1ll << 31), "tapir_gemm: M out of range");
   GemmArgs g;
@@ -57,6 +57,7 @@ int tapir_gemm(const void* a_planes, int32_t lda, int64_t a_plane_stride, const 
   g.out_f32 = out_f32; g.ldo = ldo;
   g.out_planes = static_cast<__nv_bfloat16*>(out_planes);
   g.ldp = ldp; g.out_plane_stride = out_plane_stride; g.out_P = out_P;
+  g.stats = stats; g.rows_per_frame = rows_per_frame;
   if (impl == 1) return gemm_simt(g, S(stream));
   if (impl == 0) return gemm_tc(g, S(stream));
   set_error("tapir_gemm: impl must be 0 (tcgen05) or 1 (simt)");

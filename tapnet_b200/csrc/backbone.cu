@@ -364,6 +364,18 @@ int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums
   return kOk;
 }
 
+int instnorm_zero(int frames, int C, double* sums, cudaStream_t s) {
+  TAPIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * frames * C, s));
+  return kOk;
+}
+
+int instnorm_finalize(int frames, long long hw, int C, const double* sums, float* mr, cudaStream_t s) {
+  instnorm_finalize_kernel<<<ceil_div(frames * C, 256), 256, 0, s>>>(sums, hw, frames * C, mr);
+  count_launch();
+  TAPIR_LAUNCH_CHECK("instnorm_finalize_kernel");
+  return kOk;
+}
+
 int instnorm_relu_split(const float* x, const float* mr, const float* w, const float* b,
                         int frames, long long hw, int C, __nv_bfloat16* out, long long plane_stride,
                         int planes, cudaStream_t s) {
@@ -504,6 +516,9 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
   float* x = bp.buf[0];
   TAPIR_RETURN_IF(stem_conv(video, w->stem_w, frames, H, W, x, s));
   int xi = 0;  // index of the buffer holding x
+  // InstanceNorm statistics are accumulated by the epilogue of the GEMM that produces the
+  // tensor (fp64 atomics into bp.sums); only the stem output needs the stand-alone pass.
+  bool x_stats_ready = false;
   for (int bi = 0; bi < TAPIR_NUM_RESNET_BLOCKS; ++bi) {
     const tapir_resnet_block& b = w->blocks[bi];
     const long long m_in = (long long)frames * h * wd;
@@ -513,7 +528,11 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
     float* shortcut_buf = bp.buf[(xi + 2) & 3];
     float* hbuf = bp.buf[(xi + 3) & 3];
     // bn_0 + relu -> planes
-    TAPIR_RETURN_IF(instnorm_stats(x, frames, (long long)h * wd, b.cin, bp.sums, bp.mr, s));
+    if (x_stats_ready) {
+      TAPIR_RETURN_IF(instnorm_finalize(frames, (long long)h * wd, b.cin, bp.sums, bp.mr, s));
+    } else {
+      TAPIR_RETURN_IF(instnorm_stats(x, frames, (long long)h * wd, b.cin, bp.sums, bp.mr, s));
+    }
     TAPIR_RETURN_IF(instnorm_relu_split(x, bp.mr, b.bn0_w, b.bn0_b, frames, (long long)h * wd,
                                         b.cin, bp.act, bp.act_plane, P, s));
     const float* shortcut = x;
@@ -546,9 +565,19 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
         TAPIR_RETURN_IF(im2col_s2(bp.act, bp.act_plane, frames, h, wd, b.cin, 9, bp.col, bp.col_plane, P, s));
         g.a = bp.col; g.lda = 9 * b.cin; g.a_plane_stride = bp.col_plane;
       }
+      const bool fuse = (b.stride == 1) || (((long long)oh * ow) % 128 == 0);
+      if (fuse) {
+        TAPIR_RETURN_IF(instnorm_zero(frames, b.cout, bp.sums, s));
+        g.stats = bp.sums;
+        g.rows_per_frame = oh * ow;
+      }
       TAPIR_RETURN_IF(gemm(g, s));
+      if (fuse) {
+        TAPIR_RETURN_IF(instnorm_finalize(frames, (long long)oh * ow, b.cout, bp.sums, bp.mr, s));
+      } else {
+        TAPIR_RETURN_IF(instnorm_stats(hbuf, frames, (long long)oh * ow, b.cout, bp.sums, bp.mr, s));
+      }
     }
-    TAPIR_RETURN_IF(instnorm_stats(hbuf, frames, (long long)oh * ow, b.cout, bp.sums, bp.mr, s));
     TAPIR_RETURN_IF(instnorm_relu_split(hbuf, bp.mr, b.bn1_w, b.bn1_b, frames, (long long)oh * ow,
                                         b.cout, bp.act, bp.act_plane, P, s));
     {
@@ -560,6 +589,11 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
       g.frames = frames; g.H = oh; g.W = ow; g.C = b.cout;
       g.residual = shortcut; g.ldr = b.cout;
       g.out_f32 = xnew; g.ldo = b.cout;
+      x_stats_ready = (bi + 1 < TAPIR_NUM_RESNET_BLOCKS);
+      if (x_stats_ready) {  // statistics for the next block's bn_0
+        TAPIR_RETURN_IF(instnorm_zero(frames, b.cout, bp.sums, s));
+        g.stats = bp.sums;
+      }
       TAPIR_RETURN_IF(gemm(g, s));
     }
     x = xnew;

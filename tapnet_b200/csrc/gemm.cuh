@@ -42,6 +42,8 @@ struct GemmArgs {
   int ldp = 0;
   long long out_plane_stride = 0;
   int out_P = 0;
+  double* stats = nullptr;  // optional fused per-(frame, column) sum / sum-of-squares (fp64)
+  int rows_per_frame = 0;   // plain mode: rows per frame (multiple of 128); conv: implied
   int k_logical = 0;        // un-padded K for FLOP accounting (0 = K)
   const char* tag = nullptr;  // profiling class name
 };

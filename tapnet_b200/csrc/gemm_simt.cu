@@ -87,6 +87,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
       if (g.act == 1) v = gelu_tanh(v);
       if (g.residual != nullptr) v += g.residual[m * g.ldr + n];
       if (g.out_f32 != nullptr) g.out_f32[m * g.ldo + n] = v;
+      if (g.stats != nullptr) {
+        const long long rpf = (g.mode == kGemmConv3x3) ? (long long)g.H * g.W : (g.rows_per_frame > 0 ? g.rows_per_frame : g.M);
+        double* dst = g.stats + ((m / rpf) * g.N + n) * 2;
+        atomicAdd(dst, (double)v);
+        atomicAdd(dst + 1, (double)v * v);
+      }
       if (g.out_planes != nullptr) {
         float r = v;
         for (int q = 0; q < g.out_P; ++q) {

@@ -53,6 +53,8 @@ struct TcParams {
   int ldp;
   long long out_plane_stride;
   int out_P;
+  double* stats;        // optional [frames][N][2] column (sum, sum of squares) accumulators
+  int rows_per_frame;   // rows of one frame (plain mode; conv tiles never straddle frames)
   int* err;
 };
 
@@ -76,7 +78,8 @@ struct TcCfg {
 // bias values in shared memory (staged by the warp before it waited for the accumulator).
 __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row, int col0,
                                                 const uint32_t (&acc)[32],
-                                                const float* __restrict__ bias_s) {
+                                                const float* __restrict__ bias_s, bool row_ok,
+                                                int frame, int lane) {
   const bool full = (col0 + 32 <= p.N);
   float v[32];
 #pragma unroll
@@ -92,7 +95,7 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
   }
-  if (p.residual != nullptr) {
+  if (p.residual != nullptr && row_ok) {
     const float* r = p.residual + row * (long long)p.ldr + col0;
     if (full && (p.ldr & 3) == 0) {
 #pragma unroll
@@ -106,7 +109,7 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
         if (col0 + j < p.N) v[j] += r[j];
     }
   }
-  if (p.out_f32 != nullptr) {
+  if (p.out_f32 != nullptr && row_ok) {
     float* o = p.out_f32 + row * (long long)p.ldo + col0;
     if (full && (p.ldo & 3) == 0) {
 #pragma unroll
@@ -118,7 +121,37 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
         if (col0 + j < p.N) o[j] = v[j];
     }
   }
-  if (p.out_planes != nullptr) {
+  if (p.stats != nullptr) {
+    // InstanceNorm statistics of the tensor this GEMM produces (nets.py:280-286), fused here so
+    // the activation is not re-read: per column, sum and sum of squares over this warp's 32
+    // rows by a warp transpose-reduce (lane l ends up owning column col0 + l), then one fp64
+    // atomic pair per lane.
+    float s1[32], s2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = (row_ok && col0 + j < p.N) ? v[j] : 0.f;
+      s1[j] = x;
+      s2[j] = x * x;
+    }
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+#pragma unroll
+      for (int j = 0; j < sft; ++j) {
+        const bool up = (lane & sft) != 0;
+        const float a_send = up ? s1[j] : s1[j + sft], a_keep = up ? s1[j + sft] : s1[j];
+        const float b_send = up ? s2[j] : s2[j + sft], b_keep = up ? s2[j + sft] : s2[j];
+        s1[j] = a_keep + __shfl_xor_sync(0xffffffffu, a_send, sft);
+        s2[j] = b_keep + __shfl_xor_sync(0xffffffffu, b_send, sft);
+      }
+    }
+    const int col = col0 + lane;
+    if (col < p.N) {
+      double* dst = p.stats + ((long long)frame * p.N + col) * 2;
+      atomicAdd(dst, (double)s1[0]);
+      atomicAdd(dst + 1, (double)s2[0]);
+    }
+  }
+  if (p.out_planes != nullptr && row_ok) {
     // successive bf16 terms of v: plane q holds bf16(v - sum_{r<q} plane r)
     for (int q = 0; q < p.out_P; ++q) {
       __nv_bfloat16* o = p.out_planes + q * p.out_plane_stride + row * (long long)p.ldp + col0;
@@ -282,9 +315,10 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
       const int r = q * 32 + lane;
       long long row;
       bool row_ok;
+      int frame = 0;
       if (p.mode == kGemmConv3x3) {
         const int per_frame = p.tiles_x * p.tiles_y;
-        const int frame = m_tile / per_frame;
+        frame = m_tile / per_frame;
         const int rr = m_tile % per_frame;
         const int y = (rr / p.tiles_x) * p.tileH + r / p.tileW;
         const int x = (rr % p.tiles_x) * p.tileW + r % p.tileW;
@@ -293,6 +327,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
       } else {
         row = (long long)m_tile * kBlockM + r;
         row_ok = row < p.M;
+        if (p.stats != nullptr) frame = (int)(((long long)m_tile * kBlockM) / p.rows_per_frame);
       }
       const int colbase = n0 + cbase * 32;
       if (p.bias != nullptr) {  // stage this warp's bias slice while the main loop runs
@@ -315,14 +350,14 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (col0 < p.N) {
           ptx::tmem_ld_wait();
           if (i + 1 < kChunks && col0 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 1) * 32, vb);
-          if (row_ok) store_row_chunk(p, row, col0, va, bias_w + i * 32);
+          if (row_ok || p.stats != nullptr) store_row_chunk(p, row, col0, va, bias_w + i * 32, row_ok, frame, lane);
         }
         if (i + 1 < kChunks) {
           const int col1 = col0 + 32;
           if (col1 < p.N) {
             ptx::tmem_ld_wait();
             if (i + 2 < kChunks && col1 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 2) * 32, va);
-            if (row_ok) store_row_chunk(p, row, col1, vb, bias_w + (i + 1) * 32);
+            if (row_ok || p.stats != nullptr) store_row_chunk(p, row, col1, vb, bias_w + (i + 1) * 32, row_ok, frame, lane);
           }
         }
       }
@@ -461,6 +496,12 @@ int validate_gemm_args(const GemmArgs& g) {
     TAPIR_CHECK_ARG(g.out_P >= 1 && g.out_P <= 3 && g.ldp >= g.N, "gemm: bad plane output (out_P=%d ldp=%d)", g.out_P, g.ldp);
   if (g.out_f32 != nullptr) TAPIR_CHECK_ARG(g.ldo >= g.N, "gemm: ldo=%d < N=%d", g.ldo, g.N);
   if (g.residual != nullptr) TAPIR_CHECK_ARG(g.ldr >= g.N, "gemm: ldr=%d < N=%d", g.ldr, g.N);
+  if (g.stats != nullptr) {
+    TAPIR_CHECK_ARG(g.out_planes == nullptr, "gemm: fused statistics need an fp32-only output");
+    if (g.mode == kGemmPlain)
+      TAPIR_CHECK_ARG(g.rows_per_frame > 0 && g.rows_per_frame % kBlockM == 0 && g.M % g.rows_per_frame == 0,
+                      "gemm: fused statistics need rows_per_frame %% 128 == 0 (got %d)", g.rows_per_frame);
+  }
   return kOk;
 }
 
@@ -483,6 +524,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   p.out_plane_stride = g.out_plane_stride;
   p.out_P = g.out_P;
   p.err = device_error_flag();
+  p.stats = g.stats;
+  p.rows_per_frame = g.rows_per_frame > 0 ? g.rows_per_frame : g.M;
   const int P = g.planes;
 
   if (g.mode == kGemmConv3x3) {

@@ -32,6 +32,8 @@ int stem_conv(const float* video, const float* w_packed, int frames, int H, int 
               cudaStream_t s);
 int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, float* mr,
                    cudaStream_t s);
+int instnorm_zero(int frames, int C, double* sums, cudaStream_t s);
+int instnorm_finalize(int frames, long long hw, int C, const double* sums, float* mr, cudaStream_t s);
 int instnorm_relu_split(const float* x, const float* mr, const float* w, const float* b,
                         int frames, long long hw, int C, __nv_bfloat16* out, long long plane_stride,
                         int planes, cudaStream_t s);

@@ -78,7 +78,7 @@ def make_linear(w_pl, bias):
 
 
 def gemm(a_pl, w_pl, bias=None, residual=None, gelu=False, out_f32=True, out_planes=0, impl=0,
-         conv=None):
+         conv=None, stats=None, rows_per_frame=0):
   """Runs tapir_gemm. a_pl: [P, M, K] (plain) or [P, F, H, W, C] (conv=(F,H,W,C))."""
   lib = _lib.load()
   P, n, k = w_pl.shape
@@ -96,7 +96,7 @@ def gemm(a_pl, w_pl, bias=None, residual=None, gelu=False, out_f32=True, out_pla
   opl = torch.zeros(out_planes, m, n, dtype=torch.bfloat16, device=dev) if out_planes else None
   st = lib.tapir_gemm(ptr(a_pl), lda, aps, ctypes.byref(lin), m, 1 if conv else 0, f, h, w, c,
                       ptr(residual), n if residual is not None else 0, int(gelu), ptr(o32), n,
-                      ptr(opl), n, m * n, out_planes, impl, stream())
+                      ptr(opl), n, m * n, out_planes, ptr(stats), rows_per_frame, impl, stream())
   _lib.check(st, 'tapir_gemm')
   torch.cuda.synchronize()
   return o32, opl

@@ -100,3 +100,24 @@ def test_conv3x3(case, impl):
   tol = {1: 2e-2, 2: 1e-4, 3: 2e-5}[P]
   assert torch.isfinite(o32).all()
   assert err <= tol * max(scale, 1.0)
+
+
+@pytest.mark.parametrize('impl', [1, 0], ids=['simt', 'tc'])
+@pytest.mark.parametrize('mode', ['conv', 'plain'])
+def test_fused_instance_norm_statistics(mode, impl):
+  """Epilogue-fused per-(frame, channel) sum / sum of squares of the GEMM output."""
+  g = torch.Generator().manual_seed(5)
+  Fr, H, W, Ci, Co, P = 3, 24, 32, 64, 128, 2
+  w = (torch.randn(Co, Ci * (9 if mode == 'conv' else 1), generator=g) / 8).cuda()
+  stats = torch.zeros(Fr, Co, 2, dtype=torch.float64, device='cuda')
+  x = torch.randn(Fr * H * W, Ci, generator=g).cuda()
+  x_pl = U.split(x, P)
+  if mode == 'conv':
+    o32, _ = U.gemm(x_pl.reshape(P, Fr, H, W, Ci), U.split(w, P), impl=impl, conv=(Fr, H, W, Ci), stats=stats)
+  else:
+    o32, _ = U.gemm(x_pl, U.split(w, P), impl=impl, stats=stats, rows_per_frame=H * W)
+  out = o32.double().reshape(Fr, H * W, Co)
+  ref = torch.stack([out.sum(1), (out * out).sum(1)], -1)
+  err = ((stats - ref).abs() / ref.abs().clamp(min=1.0)).max().item()
+  U.record(f'gemm_stats_{mode}_impl{impl}', rel_err=err)
+  assert err < 1e-5
