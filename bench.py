@@ -41,8 +41,9 @@ def _peaks():
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons during the timed region."""
-  Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+  """nvidia-smi clocks / throttle reasons; started before warm-up, samples are kept only if
+  their timestamp falls inside the timed region (mark_begin .. mark_end)."""
+  Q = ('timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
        'clocks_event_reasons.sw_power_cap')
 
@@ -50,12 +51,13 @@ class ClockSampler:
     self.index = index
     self.proc = None
     self.lines = []
+    self.t0 = self.t1 = None
 
   def start(self):
     try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-           '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+           '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
     except OSError:
@@ -63,32 +65,51 @@ class ClockSampler:
 
   def _read(self):
     for line in self.proc.stdout:
-      self.lines.append(line.strip())
+      self.lines.append((time.time(), line.strip()))
+
+  def mark_begin(self):
+    self.t0 = time.time()
+
+  def mark_end(self):
+    self.t1 = time.time()
 
   def stop(self):
     if self.proc is None:
       return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+    time.sleep(0.05)
     self.proc.terminate()
     try:
       self.proc.wait(timeout=5)
     except subprocess.TimeoutExpired:
       self.proc.kill()
-    sm, mx, reasons = [], None, set()
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for ln in self.lines:
-      parts = [p.strip() for p in ln.split(',')]
-      if len(parts) < 6:
-        continue
-      try:
-        sm.append(float(parts[0]))
-        mx = float(parts[1])
-      except ValueError:
-        continue
-      for n, v in zip(names, parts[2:6]):
-        if v.lower().startswith('active'):
-          reasons.add(n)
+
+    def parse(window):
+      sm, mx, reasons = [], None, set()
+      for ts, ln in self.lines:
+        if window and not (self.t0 - 0.02 <= ts <= self.t1 + 0.05):
+          continue
+        parts = [p.strip() for p in ln.split(',')]
+        if len(parts) < 7:
+          continue
+        try:
+          sm.append(float(parts[1]))
+          mx = float(parts[2])
+        except ValueError:
+          continue
+        for n, v in zip(names, parts[3:7]):
+          if v.lower().startswith('active'):
+            reasons.add(n)
+      return sm, mx, reasons
+
+    sm, mx, reasons = parse(True)
+    where = 'timed region'
+    if not sm:  # region shorter than the sampling period: fall back to the whole run under load
+      sm, mx, reasons = parse(False)
+      sm = [v for v in sm if mx and v > 0.5 * mx] or sm
+      where = 'whole run (timed region shorter than the sampling period)'
     return dict(sm_mhz=(statistics.median(sm) if sm else None), sm_max_mhz=mx,
-                reasons=sorted(reasons), samples=len(sm))
+                reasons=sorted(reasons), samples=len(sm), window=where)
 
 
 def build_inputs(world):
@@ -168,14 +189,16 @@ def run_ours(args):
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.item() / steps
 
-  for _ in range(max(args.warmup, 3)):
-    step_device()
-  barrier()
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
+  for _ in range(max(args.warmup, 3)):
+    step_device()
+  barrier()
   launches0 = lib.tapir_launch_count()
+  sampler.mark_begin()
   ms_step = timed(step_device, args.steps)
+  sampler.mark_end()
   launches = (lib.tapir_launch_count() - launches0) // max(args.steps, 1)
   clocks = sampler.stop() if rank == 0 else None
   step_e2e()
@@ -355,7 +378,7 @@ def run_reference(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=10)
+  ap.add_argument('--steps', type=int, default=20)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--precision', default='bf16x3', choices=['bf16', 'bf16x3', 'bf16x6'])

@@ -210,7 +210,8 @@ struct DwParams {
 };
 
 __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
-  extern __shared__ float dw_smem[];  // [kDwRows][512] LN'd rows, later reused for z
+  extern __shared__ float dw_smem[];  // [kDwRows][512] LN'd rows (recycled for z) + [kDwTile][512] raw x
+  float* xraw = dw_smem + kDwRows * 512;
   const int n = blockIdx.y;
   const int t0 = blockIdx.x * kDwTile;
   const int t1 = min(t0 + kDwTile, p.T);
@@ -247,6 +248,8 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
         reinterpret_cast<float4*>(dst)[i * 32 + lane] =
             make_float4((v[i].x - mean) * rstd * ww.x, (v[i].y - mean) * rstd * ww.y,
                         (v[i].z - mean) * rstd * ww.z, (v[i].w - mean) * rstd * ww.w);
+        // keep the raw row for the skip connection: the frame loop below must not wait on L2
+        if (t >= t0 && t < t1) reinterpret_cast<float4*>(xraw + (t - t0) * 512)[i * 32 + lane] = v[i];
       }
     } else if (p.causal && p.ctx1_in != nullptr && t >= -2 && t < 0) {
       // context frames -2, -1 of the layer-normed input
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
   for (int i = 0; i < t1 - t0; ++i) {
     const int t = t0 + i;
     h1(first + 2 + i, hc);
-    float acc = xn[(long long)t * 512 + c];
+    float acc = xraw[i * 512 + c];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       acc += fmaf(w2[j][2], hc[j], fmaf(w2[j][1], hb[j], fmaf(w2[j][0], ha[j], b2[j])));
@@ -505,7 +508,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     return kWorkspaceTooSmall;
   }
   static bool configured = false;
-  const int dw_smem = kDwRows * 512 * (int)sizeof(float);
+  const int dw_smem = (kDwRows + kDwTile) * 512 * (int)sizeof(float);
   if (!configured) {
     TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
     configured = true;
