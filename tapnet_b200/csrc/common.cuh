@@ -122,6 +122,19 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 (&out)[P]) {
   }
 }
 
+// Same split step with integer-ALU rounding only (round-to-nearest-even on the raw bits).  On
+// sm_100 both F2F and F2FP go through the variable-latency conversion unit; in the GEMM
+// epilogue their scoreboard stalls dominated (ncu: 30 % of samples on the dependent shift), so
+// the hot epilogue rounds with IADD3/LOP3/PRMT instead.  Bit-identical to cvt.rn for finite x.
+__device__ __forceinline__ uint32_t bf16x2_split_alu(float& a, float& b) {
+  uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  ua = (ua + 0x7fffu + ((ua >> 16) & 1u)) & 0xffff0000u;
+  ub = (ub + 0x7fffu + ((ub >> 16) & 1u)) & 0xffff0000u;
+  a -= __uint_as_float(ua);
+  b -= __uint_as_float(ub);
+  return __byte_perm(ua, ub, 0x7632);  // low half = bf16(a), high half = bf16(b)
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }

@@ -159,10 +159,10 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           uint4 w;
-          w.x = bf16x2_split(v[j], v[j + 1]);
-          w.y = bf16x2_split(v[j + 2], v[j + 3]);
-          w.z = bf16x2_split(v[j + 4], v[j + 5]);
-          w.w = bf16x2_split(v[j + 6], v[j + 7]);
+          w.x = bf16x2_split_alu(v[j], v[j + 1]);
+          w.y = bf16x2_split_alu(v[j + 2], v[j + 3]);
+          w.z = bf16x2_split_alu(v[j + 4], v[j + 5]);
+          w.w = bf16x2_split_alu(v[j + 6], v[j + 7]);
           *reinterpret_cast<uint4*>(o + j) = w;
         }
       } else {
