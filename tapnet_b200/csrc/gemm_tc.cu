@@ -56,6 +56,7 @@ struct TcParams {
   double* stats;        // optional [frames][N][2] column (sum, sum of squares) accumulators
   int rows_per_frame;   // rows of one frame (plain mode; conv tiles never straddle frames)
   int* err;
+  int debug_mode;       // bring-up only: 1 = epilogue skips TMEM loads and stores, 2 = loads but no math/stores
 };
 
 template <int BLOCK_N, int P>
@@ -365,6 +366,12 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + cbase * 32;
       uint32_t va[32], vb[32];
+      if (p.debug_mode == 1) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
       if (colbase < p.N) ptx::tmem_ld_32x32(taddr, va);  // all conditions are warp-uniform
 #pragma unroll
       for (int i = 0; i < kChunks; i += 2) {
@@ -372,14 +379,14 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (col0 < p.N) {
           ptx::tmem_ld_wait();
           if (i + 1 < kChunks && col0 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 1) * 32, vb);
-          epilogue_chunk(p, tr, q, lane, stage_w, va, col0, bias_r[i]);
+          if (p.debug_mode != 2) epilogue_chunk(p, tr, q, lane, stage_w, va, col0, bias_r[i]);
         }
         if (i + 1 < kChunks) {
           const int col1 = col0 + 32;
           if (col1 < p.N) {
             ptx::tmem_ld_wait();
             if (i + 2 < kChunks && col1 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 2) * 32, va);
-            epilogue_chunk(p, tr, q, lane, stage_w, vb, col1, bias_r[i + 1]);
+            if (p.debug_mode != 2) epilogue_chunk(p, tr, q, lane, stage_w, vb, col1, bias_r[i + 1]);
           }
         }
       }
@@ -547,6 +554,11 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   p.out_plane_stride = g.out_plane_stride;
   p.out_P = g.out_P;
   p.err = device_error_flag();
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TAPIR_B200_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug_mode = dbg;
+  }
   p.stats = g.stats;
   p.rows_per_frame = g.rows_per_frame > 0 ? g.rows_per_frame : g.M;
   const int P = g.planes;

@@ -120,4 +120,4 @@ def test_fused_instance_norm_statistics(mode, impl):
   ref = torch.stack([out.sum(1), (out * out).sum(1)], -1)
   err = ((stats - ref).abs() / ref.abs().clamp(min=1.0)).max().item()
   U.record(f'gemm_stats_{mode}_impl{impl}', rel_err=err)
-  assert err < 1e-5
+  assert err < 5e-5
