@@ -1,11 +1,12 @@
 // tcgen05 / TMEM / TMA split-bf16 GEMM and implicit-GEMM 3x3 convolution for sm_100a.
 //
-// One persistent CTA per SM, 10 warps:
+// One persistent CTA per SM, 2 + 4*G warps (G = column groups of the epilogue, 16 epilogue warps for
+// BLOCK_N >= 128):
 //   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor tiles of A and B planes into a
 //                      multi-stage shared-memory ring (128B-swizzled, K-major)
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16,
 //                      fp32 accumulators in TMEM (double buffered: 2 x BLOCK_N columns)
-//   warps 2..9         epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row
+//   warps 2..          epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row
 //                      per thread), bias / tanh-GELU / residual, store fp32 and/or bf16 planes
 // Pipelines: full/empty mbarriers between TMA and MMA, tmem_full/tmem_empty between MMA and
 // epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -29,8 +30,13 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kNumEpilogueWarps = 8;
-constexpr int kThreads = 64 + 32 * kNumEpilogueWarps;
+// Epilogue warps: 4 TMEM lane quadrants x G column groups.  The epilogue is latency bound
+// (conversions, MUFU, TMEM loads), so it needs thread-level parallelism: with the accumulator
+// tile split over 16 warps it hides behind a K=512 main loop; measured on the mixer `up` GEMM
+// (12288 x 2048 x 512): main loop alone 54 us, with 8 epilogue warps 85 us.
+__host__ __device__ constexpr int epi_groups(int block_n) { return block_n >= 128 ? 4 : block_n / 32; }
+__host__ __device__ constexpr int epi_warps(int block_n) { return 4 * epi_groups(block_n); }
+__host__ __device__ constexpr int num_threads(int block_n) { return 64 + 32 * epi_warps(block_n); }
 constexpr int kNumAccStages = 2;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kBarrierBytes = 256;
@@ -42,7 +48,7 @@ struct TcParams {
   int num_k_blocks;
   int num_m_tiles, num_n_tiles;
   int mode;
-  int H, W, cblocks, tileW, tileH, tiles_x, tiles_y, tw_shift;
+  int H, W, cblocks, tileW, tileH, tiles_x, tiles_y;
   const float* bias;
   const float* residual;
   int ldr;
@@ -56,7 +62,7 @@ struct TcParams {
   double* stats;        // optional [frames][N][2] column (sum, sum of squares) accumulators
   int rows_per_frame;   // rows of one frame (plain mode; conv tiles never straddle frames)
   int* err;
-  int debug_mode;       // bring-up only: 1 = epilogue skips TMEM loads and stores, 2 = loads but no math/stores
+  int debug_mode;       // bring-up only: 1 = epilogue skips TMEM loads and stores
 };
 
 template <int BLOCK_N, int P>
@@ -64,140 +70,127 @@ struct TcCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = P * (kABytes + kBBytes);
-  static constexpr int kBiasBytes = 0;  // bias lives in registers (4 values per lane and chunk)
-  static constexpr int kStagingBytes = kNumEpilogueWarps * 32 * 32 * 4;     // per-warp transpose buffer
-  static constexpr int kAvail = kSmemLimit - 1024 - kBarrierBytes - kBiasBytes - kStagingBytes;
+  static constexpr int kEpiWarps = epi_warps(BLOCK_N);
+  static constexpr int kChunks = BLOCK_N / 32 / epi_groups(BLOCK_N);  // 32-column chunks per warp
+  static constexpr int kBiasBytes = kEpiWarps * kChunks * 32 * 4;  // per-warp bias slice
+  static constexpr int kAvail = kSmemLimit - 1024 - kBarrierBytes - kBiasBytes;
   static constexpr int kStagesRaw = kAvail / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarrierBytes + kBiasBytes + kStagingBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarrierBytes + kBiasBytes;
   static constexpr int kTmemCols = (kNumAccStages * BLOCK_N <= 128) ? 128
                                    : (kNumAccStages * BLOCK_N <= 256) ? 256 : 512;
   static_assert(kStages >= 1, "tile does not fit in shared memory");
   static_assert(kStages * 2 + 2 * kNumAccStages <= (kBarrierBytes - 16) / 8, "barrier space");
 };
 
-// Maps a tile-local row index to the output row (and whether it exists).
-struct TileRows {
-  int mode;
-  long long m0;
-  int M;
-  int frame, y0, x0, H, W, tw_shift, tw_mask;
-};
-__device__ __forceinline__ bool tile_row(const TileRows& t, int r, long long* row) {
-  if (t.mode == kGemmConv3x3) {
-    const int y = t.y0 + (r >> t.tw_shift), x = t.x0 + (r & t.tw_mask);
-    *row = ((long long)t.frame * t.H + y) * t.W + x;
-    return y < t.H && x < t.W;
+// One output row (this thread) x 32 consecutive columns.  `bias_s` points at this chunk's 32
+// bias values in shared memory (staged by the warp before it waited for the accumulator).
+__device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row, int col0,
+                                                const uint32_t (&acc)[32],
+                                                const float* __restrict__ bias_s, bool row_ok,
+                                                int frame, int lane) {
+  const bool full = (col0 + 32 <= p.N);
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + j);  // broadcast LDS.128
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
   }
-  *row = t.m0 + r;
-  return *row < t.M;
-}
-
-// Epilogue of one 32-row x 32-column accumulator block owned by one warp.  tcgen05.ld hands
-// every thread one ROW (32 consecutive columns); storing that directly costs 32 partial
-// cache lines per store instruction (measured: the epilogue, not the MMA, bounded every GEMM
-// with K <= 1024).  The block is therefore transposed through a 4 KB swizzled shared-memory
-// buffer so that 8 consecutive lanes own 128 contiguous bytes of one row: bias / GELU /
-// residual / statistics / plane split then run in that layout and every global access is a
-// full line.
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const TileRows& tr, int q, int lane,
-                                               float* __restrict__ stage,
-                                               const uint32_t (&acc)[32], int col0,
-                                               const float (&b4)[4]) {
-  {
-    const int sw = lane & 7;
-    uint4* dst = reinterpret_cast<uint4*>(stage + lane * 32);
+  if (p.act == 1) {
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4)
-      dst[c4 ^ sw] = make_uint4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
   }
-  __syncwarp();
-  const int rr = lane >> 3, cc = lane & 7;
-  const int col = col0 + 4 * cc;
-  int nvalid = p.N - col;
-  nvalid = nvalid < 0 ? 0 : (nvalid > 4 ? 4 : nvalid);
-  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.residual != nullptr && row_ok) {
+    const float* r = p.residual + row * (long long)p.ldr + col0;
+    if (full && (p.ldr & 3) == 0) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int rl = 4 * k + rr;
-    const float4 t = *reinterpret_cast<const float4*>(stage + rl * 32 + ((cc ^ (rl & 7)) << 2));
-    float x[4] = {t.x + b4[0], t.y + b4[1], t.z + b4[2], t.w + b4[3]};
-    if (p.act == 1) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) x[e] = gelu_tanh(x[e]);
-    }
-    long long row;
-    const bool ok = tile_row(tr, q * 32 + rl, &row) && nvalid > 0;
-    if (!ok) continue;
-    if (p.residual != nullptr) {
-      const float* r = p.residual + row * (long long)p.ldr + col;
-      if (nvalid == 4 && (p.ldr & 3) == 0) {
-        const float4 rv = *reinterpret_cast<const float4*>(r);
-        x[0] += rv.x; x[1] += rv.y; x[2] += rv.z; x[3] += rv.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (e < nvalid) x[e] += r[e];
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = *reinterpret_cast<const float4*>(r + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
-    }
-    if (p.stats != nullptr) {
+    } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (e < nvalid) { s1[e] += x[e]; s2[e] = fmaf(x[e], x[e], s2[e]); }
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] += r[j];
     }
-    if (p.out_f32 != nullptr) {
-      float* o = p.out_f32 + row * (long long)p.ldo + col;
-      if (nvalid == 4 && (p.ldo & 3) == 0) {
-        *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-      } else {
+  }
+  if (p.out_f32 != nullptr && row_ok) {
+    float* o = p.out_f32 + row * (long long)p.ldo + col0;
+    if (full && (p.ldo & 3) == 0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (e < nvalid) o[e] = x[e];
-      }
-    }
-    if (p.out_planes != nullptr) {
-      // successive bf16 terms: plane j holds bf16(x - sum of the earlier planes)
-      for (int j = 0; j < p.out_P; ++j) {
-        __nv_bfloat16* o = p.out_planes + j * p.out_plane_stride + row * (long long)p.ldp + col;
-        uint2 w;
-        w.x = bf16x2_split(x[0], x[1]);
-        w.y = bf16x2_split(x[2], x[3]);
-        if (nvalid == 4 && (p.ldp & 3) == 0) {
-          *reinterpret_cast<uint2*>(o) = w;
-        } else {
-          const uint32_t u[2] = {w.x, w.y};
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (e < nvalid) o[e] = __ushort_as_bfloat16((unsigned short)(u[e >> 1] >> (16 * (e & 1))));
-        }
-      }
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) o[j] = v[j];
     }
   }
   if (p.stats != nullptr) {
-    // InstanceNorm statistics of the produced tensor (nets.py:280-286): the 4 lanes that share
-    // a column group add up their 8 rows each, then one fp64 atomic pair per column.
+    // InstanceNorm statistics of the tensor this GEMM produces (nets.py:280-286), fused here so
+    // the activation is not re-read: per column, sum and sum of squares over this warp's 32
+    // rows by a warp transpose-reduce (lane l ends up owning column col0 + l), then one fp64
+    // atomic pair per lane.
+    // two passes (sum, then sum of squares) so only one 32-entry scratch array is live
+    float tot[2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
-      s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8);
-      s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
-      s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
-    }
-    if (lane < 8) {
+    for (int pass = 0; pass < 2; ++pass) {
+      float t[32];
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (e < nvalid) {
-          double* dst = p.stats + ((long long)tr.frame * p.N + col + e) * 2;
-          atomicAdd(dst, (double)s1[e]);
-          atomicAdd(dst + 1, (double)s2[e]);
+      for (int j = 0; j < 32; ++j) {
+        const float x = (row_ok && col0 + j < p.N) ? v[j] : 0.f;
+        t[j] = pass == 0 ? x : x * x;
+      }
+#pragma unroll
+      for (int sft = 16; sft >= 1; sft >>= 1) {
+#pragma unroll
+        for (int j = 0; j < sft; ++j) {
+          const bool up = (lane & sft) != 0;
+          const float send = up ? t[j] : t[j + sft], keep = up ? t[j + sft] : t[j];
+          t[j] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
         }
+      }
+      tot[pass] = t[0];
+    }
+    const int col = col0 + lane;
+    if (col < p.N) {
+      double* dst = p.stats + ((long long)frame * p.N + col) * 2;
+      atomicAdd(dst, (double)tot[0]);
+      atomicAdd(dst + 1, (double)tot[1]);
     }
   }
-  __syncwarp();  // the staging buffer is rewritten by the next chunk
+  if (p.out_planes != nullptr && row_ok) {
+    // successive bf16 terms of v: plane q holds bf16(v - sum_{r<q} plane r)
+    for (int q = 0; q < p.out_P; ++q) {
+      __nv_bfloat16* o = p.out_planes + q * p.out_plane_stride + row * (long long)p.ldp + col0;
+      if (full && (p.ldp & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 w;
+          w.x = bf16x2_split(v[j], v[j + 1]);
+          w.y = bf16x2_split(v[j + 2], v[j + 3]);
+          w.z = bf16x2_split(v[j + 4], v[j + 5]);
+          w.w = bf16x2_split(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(o + j) = w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+          v[j] -= __bfloat162float(h);
+          if (col0 + j < p.N) o[j] = h;
+        }
+      }
+    }
+  }
 }
 
 template <int BLOCK_N, int P>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(num_threads(BLOCK_N), 1)
 gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<BLOCK_N, P>;
   extern __shared__ uint8_t smem_raw[];
@@ -210,7 +203,6 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
   uint64_t* tmem_empty_bar = tmem_full_bar + kNumAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kNumAccStages);
   float* bias_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + kBarrierBytes);
-  float* staging_smem = bias_smem + Cfg::kBiasBytes / 4;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -222,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     }
     for (int a = 0; a < kNumAccStages; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], kNumEpilogueWarps);  // one arrive per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[a], Cfg::kEpiWarps);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tmA);
@@ -319,48 +311,45 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------------ epilogue
-    // 8 warps: TMEM lane quadrant q = warp % 4 (hardware restriction: a warp may only touch
-    // lanes [32*(warp%4), +32)), column half = (warp - 2) / 4.  TMEM loads are software
+    // TMEM lane quadrant q = warp % 4 (hardware restriction: a warp may only touch lanes
+    // [32*(warp%4), +32)), column group = (warp - 2) / 4.  TMEM loads are software
     // pipelined: chunk i+1 is in flight while chunk i goes through bias / GELU / stores.
-    constexpr int kChunks = BLOCK_N / 64;  // 32-column chunks per warp
+    constexpr int kChunks = Cfg::kChunks;
     const int q = warp & 3;
     const int cbase = ((warp - 2) >> 2) * kChunks;
-    float* stage_w = staging_smem + (warp - 2) * (32 * 32);
+    float* bias_w = bias_smem + (warp - 2) * (kChunks * 32);  // private to this warp
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m_tile = tile / p.num_n_tiles;
       const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-      TileRows tr;
-      tr.mode = p.mode;
-      tr.M = p.M;
-      tr.H = p.H;
-      tr.W = p.W;
-      tr.tw_shift = p.tw_shift;
-      tr.tw_mask = p.tileW - 1;
-      tr.m0 = (long long)m_tile * kBlockM;
-      tr.frame = 0;
-      tr.y0 = tr.x0 = 0;
+      const int r = q * 32 + lane;
+      long long row;
+      bool row_ok;
+      int frame = 0;
       if (p.mode == kGemmConv3x3) {
         const int per_frame = p.tiles_x * p.tiles_y;
-        tr.frame = m_tile / per_frame;
+        frame = m_tile / per_frame;
         const int rr = m_tile % per_frame;
-        tr.y0 = (rr / p.tiles_x) * p.tileH;
-        tr.x0 = (rr % p.tiles_x) * p.tileW;
-      } else if (p.stats != nullptr) {
-        tr.frame = (int)(tr.m0 / p.rows_per_frame);
+        const int y = (rr / p.tiles_x) * p.tileH + r / p.tileW;
+        const int x = (rr % p.tiles_x) * p.tileW + r % p.tileW;
+        row_ok = (y < p.H) && (x < p.W);
+        row = ((long long)frame * p.H + y) * p.W + x;
+      } else {
+        row = (long long)m_tile * kBlockM + r;
+        row_ok = row < p.M;
+        if (p.stats != nullptr) frame = (int)(((long long)m_tile * kBlockM) / p.rows_per_frame);
       }
       const int colbase = n0 + cbase * 32;
-      // this lane's 4 bias values per chunk (columns 4*(lane%8)..+3), fetched before the wait
-      float bias_r[kChunks][4];
+      if (p.bias != nullptr) {  // stage this warp's bias slice while the main loop runs
+        __syncwarp();
 #pragma unroll
-      for (int j = 0; j < kChunks; ++j) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = colbase + j * 32 + 4 * (lane & 7) + e;
-          bias_r[j][e] = (p.bias != nullptr && c < p.N) ? __ldg(p.bias + c) : 0.f;
+        for (int j = 0; j < kChunks; ++j) {
+          const int c = colbase + j * 32 + lane;
+          bias_w[j * 32 + lane] = (c < p.N) ? __ldg(p.bias + c) : 0.f;
         }
+        __syncwarp();
       }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 104);
       ptx::tc_fence_after();
@@ -379,14 +368,14 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (col0 < p.N) {
           ptx::tmem_ld_wait();
           if (i + 1 < kChunks && col0 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 1) * 32, vb);
-          if (p.debug_mode != 2) epilogue_chunk(p, tr, q, lane, stage_w, va, col0, bias_r[i]);
+          if (row_ok || p.stats != nullptr) store_row_chunk(p, row, col0, va, bias_w + i * 32, row_ok, frame, lane);
         }
         if (i + 1 < kChunks) {
           const int col1 = col0 + 32;
           if (col1 < p.N) {
             ptx::tmem_ld_wait();
             if (i + 2 < kChunks && col1 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 2) * 32, va);
-            if (p.debug_mode != 2) epilogue_chunk(p, tr, q, lane, stage_w, vb, col1, bias_r[i + 1]);
+            if (row_ok || p.stats != nullptr) store_row_chunk(p, row, col1, vb, bias_w + (i + 1) * 32, row_ok, frame, lane);
           }
         }
       }
@@ -480,7 +469,7 @@ int launch(const TcParams& p, const GemmArgs& g, cudaStream_t stream) {
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BLOCK_N, P><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
+  gemm_tc_kernel<BLOCK_N, P><<<grid, num_threads(BLOCK_N), Cfg::kSmemBytes, stream>>>(p);
   count_launch();
   TAPIR_LAUNCH_CHECK("gemm_tc_kernel");
   return kOk;
@@ -490,10 +479,10 @@ int pick_block_n(int m_tiles, int N, int P) {
   const char* force = getenv("TAPIR_B200_BLOCK_N");
   if (force != nullptr) {
     int v = atoi(force);
-    if (v == 64 || v == 128 || (v == 256 && P <= 1)) return v;
+    if (v == 64 || v == 128 || (v == 256 && P <= 2)) return v;
   }
   if (N <= 64) return 64;
-  if (P >= 2 || N <= 128) return 128;  // 256-wide tiles only have room for 1-2 stages at P >= 2
+  return 128;  // 256-wide tiles gave no measurable gain (scripts/gemm_bench.py) and spill at 16 epilogue warps
   // fewest (waves x tile width); 256-wide tiles re-read A half as often, so prefer on ties
   const int sms = num_sms();
   const long long c128 = (long long)ceil_div(m_tiles * ceil_div(N, 128), sms) * 128;
@@ -541,7 +530,6 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   p.M = g.M;
   p.N = g.N;
   p.num_k_blocks = g.K / kBlockK;
-  p.tileW = 1;
   p.mode = g.mode;
   p.bias = g.bias;
   p.residual = g.residual;
@@ -565,8 +553,6 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
 
   if (g.mode == kGemmConv3x3) {
     choose_conv_tile(g.H, g.W, &p.tileW, &p.tileH);
-    p.tw_shift = 0;
-    while ((1 << p.tw_shift) < p.tileW) ++p.tw_shift;
     p.H = g.H;
     p.W = g.W;
     p.cblocks = g.C / kBlockK;
@@ -601,7 +587,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   if (bn == BN && P == PP) return launch<BN, PP>(p, g, stream);
   TAPIR_TC_CASE(64, 1) TAPIR_TC_CASE(64, 2) TAPIR_TC_CASE(64, 3)
   TAPIR_TC_CASE(128, 1) TAPIR_TC_CASE(128, 2) TAPIR_TC_CASE(128, 3)
-  TAPIR_TC_CASE(256, 1)
+  TAPIR_TC_CASE(256, 1) TAPIR_TC_CASE(256, 2)
 #undef TAPIR_TC_CASE
   set_error("gemm_tc: no kernel for BLOCK_N=%d planes=%d", bn, P);
   return kUnsupported;
