@@ -136,6 +136,7 @@ class TAPIR(nn.Module):
     self._packed = None
     self._packed_sig = None
     self._ws = {}
+    self._consts = {}
 
   # ------------------------------------------------------------------ parameter plumbing
   def _register(self, key, tensor):
@@ -175,6 +176,15 @@ class TAPIR(nn.Module):
 
   def _stream(self):
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+  def _const(self, values, dev):
+    """Small constant vectors, cached: creating them per call costs a blocking H2D copy."""
+    key = (tuple(float(v) for v in values), str(dev))
+    t = self._consts.get(key)
+    if t is None:
+      t = torch.tensor(key[0], dtype=torch.float32, device=dev)
+      self._consts[key] = t
+    return t
 
   def _workspace(self, name, nbytes, dev):
     ws = self._ws.get(name)
@@ -496,11 +506,10 @@ class TAPIR(nn.Module):
         if query_points_in_video is not None:
           qp = query_points_in_video[bi, sl].to(torch.float32)
           # utils.convert_grid_coordinates (coords * out / in), tapir_model.py:488-493
-          scale_o = torch.tensor([T, ih, iw], dtype=torch.float32, device=dev)
-          scale_i = torch.tensor([T, vh, vw], dtype=torch.float32, device=dev)
-          qp = (qp * scale_o / scale_i).contiguous()
+          qp = (qp * self._const([T, ih, iw], dev) / self._const([T, vh, vw], dev)).contiguous()
         pos = new(n, T, 2)
-        occ0, expd0 = new(n, T), new(n, T)
+        # outputs are written in place: [bi, q0:q0+n] slices of the result tensors are contiguous
+        occ0, expd0 = occ_out[0][bi, sl], expd_out[0][bi, sl]
         nbytes = lib.tapir_cost_volume_workspace_bytes(n, T, gh0, gw0, c0)
         ws = self._workspace('cost_volume', nbytes, dev)
         _lib.check(lib.tapir_cost_volume_tracks(
@@ -508,16 +517,14 @@ class TAPIR(nn.Module):
             float(self.softmax_temperature), ih, iw, _ptr(pos), _ptr(occ0), _ptr(expd0), None,
             _ptr(ws), ws.numel(), stream), 'tapir_cost_volume_tracks')
         # train2orig (tapir_model.py:435-441)
-        scale = torch.tensor([vw / 1.0, vh / 1.0], dtype=torch.float32, device=dev)
-        trk_out[0][bi, sl] = pos * scale / torch.tensor([float(iw), float(ih)], device=dev)
-        occ_out[0][bi, sl] = occ0
-        expd_out[0][bi, sl] = expd0
+        torch.div(pos * self._const([vw, vh], dev), self._const([iw, ih], dev),
+                  out=trk_out[0][bi, sl])
 
         # ---- refinement iterations
         x_planes = new(P, rows, kin, dtype=torch.bfloat16)
         res = new(rows, 388)
         feats = [new(n, T, 384), new(n, T, 384)]
-        occ, expd = occ0.clone(), expd0.clone()
+        occ, expd = occ0, expd0
         nbytes = lib.tapir_mixer_workspace_bytes(rows, P)
         mws = self._workspace('mixer', nbytes, dev)
         have_feats = False
@@ -569,18 +576,14 @@ class TAPIR(nn.Module):
             io.ctx2_in = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in c2])
           o1 = o2 = None
           if get_causal_context:
-            o1 = [new(n, 2, 512) for _ in range(nb)]
-            o2 = [new(n, 2, 2048) for _ in range(nb)]
+            o1 = [new_ctx[it][f'block_{i}_causal_1'][bi, sl] for i in range(nb)]
+            o2 = [new_ctx[it][f'block_{i}_causal_2'][bi, sl] for i in range(nb)]
             io.ctx1_out = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in o1])
             io.ctx2_out = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in o2])
           io.out = res.data_ptr()
           io.ldo = 388
           _lib.check(lib.tapir_mixer_forward(ctypes.byref(pk['mixer']), ctypes.byref(io), _ptr(mws),
                                              mws.numel(), stream), 'tapir_mixer_forward')
-          if get_causal_context:
-            for i in range(nb):
-              new_ctx[it][f'block_{i}_causal_1'][bi, sl] = o1[i]
-              new_ctx[it][f'block_{i}_causal_2'][bi, sl] = o2[i]
 
           ua = _lib.UpdateArgs()
           ua.res, ua.ld_res = res.data_ptr(), 388
@@ -592,8 +595,8 @@ class TAPIR(nn.Module):
           ua.feat_hi, ua.feat_hi_stride_n, ua.feat_hi_stride_t = fh
           ua.feat_lo, ua.feat_lo_stride_n, ua.feat_lo_stride_t = fl
           nxt = 1 - cur if have_feats else cur
-          trk_i = new(n, T, 2)
-          occ_n, expd_n = new(n, T), new(n, T)
+          trk_i = trk_out[it + 1][bi, sl]
+          occ_n, expd_n = occ_out[it + 1][bi, sl], expd_out[it + 1][bi, sl]
           ua.pos = pos.data_ptr()
           ua.occ_in, ua.expd_in = occ.data_ptr(), expd.data_ptr()
           ua.occ_out, ua.expd_out = occ_n.data_ptr(), expd_n.data_ptr()
@@ -603,14 +606,11 @@ class TAPIR(nn.Module):
           cur = nxt
           have_feats = True
           occ, expd = occ_n, expd_n
-          trk_out[it + 1][bi, sl] = trk_i
-          occ_out[it + 1][bi, sl] = occ
-          expd_out[it + 1][bi, sl] = expd
           if (it + 1) % self.num_pips_iter == 0:
             # level boundary (tapir_model.py:549-552): features restart from the query,
             # occlusion / expected_dist revert to the stage-A estimate, positions carry over
             have_feats = False
-            occ, expd = occ0.clone(), expd0.clone()
+            occ, expd = occ0, expd0
           del holders
 
     out = dict(occlusion=occ_out, tracks=trk_out, expected_dist=expd_out)
