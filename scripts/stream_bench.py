@@ -54,8 +54,32 @@ e1.record()
 torch.cuda.synchronize()
 wall = time.perf_counter() - t0
 ms = e0.elapsed_time(e1)
-print(json.dumps(dict(config='causal BootsTAPIR streaming 256x256', frames=a.frames, queries=a.queries,
+eager = dict(config='causal BootsTAPIR streaming 256x256', frames=a.frames, queries=a.queries,
                       ms_per_frame_device=round(ms / a.frames, 3), ms_per_frame_wall=round(wall * 1e3 / a.frames, 3),
                       frames_per_s=round(a.frames / wall, 1),
                       point_frames_per_s=round(a.frames * a.queries / wall, 1),
+                      finite=bool(torch.isfinite(tracks).all()))
+print(json.dumps(dict(mode='eager', **eager)))
+
+# CUDA-graph replay of the same per-frame step
+from tapnet_b200 import streaming  # noqa: E402
+
+trk = streaming.OnlineTracker(model, 256, 256, a.queries)
+trk.init(clip[0, 0], q)
+for t in range(a.warm):
+  trk.step(clip[0, t % 16])
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+e0.record()
+for t in range(a.frames):
+  tracks, vis = trk.step(clip[0, (a.warm + t) % 16])
+e1.record()
+torch.cuda.synchronize()
+wall = time.perf_counter() - t0
+ms = e0.elapsed_time(e1)
+print(json.dumps(dict(mode='cuda-graph', config='causal BootsTAPIR streaming 256x256', frames=a.frames,
+                      queries=a.queries, ms_per_frame_device=round(ms / a.frames, 3),
+                      ms_per_frame_wall=round(wall * 1e3 / a.frames, 3), frames_per_s=round(a.frames / wall, 1),
+                      point_frames_per_s=round(a.frames * a.queries / wall, 1),
                       finite=bool(torch.isfinite(tracks).all()))))
+

@@ -100,6 +100,29 @@ def test_c5_hires_1024_against_oracle_reduced_clip():
   assert e_t <= 4e-3 and e_o <= 1e-4 and e_e <= 1e-4
 
 
+def test_c3_graph_replay_tracker_equals_eager_streaming():
+  """tapnet_b200.streaming.OnlineTracker (CUDA-graph replay) == eager per-frame calls, bit for bit."""
+  from tapnet_b200 import streaming
+  model, _, _ = get_model(causal=True)
+  T, N = 5, 64
+  video = synth.make_video(T).cuda()
+  q = synth.make_queries(N, T, frame0_only=True).cuda()
+  trk = streaming.OnlineTracker(model, 256, 256, N)
+  qf = trk.init(video[0, 0], q)
+  state = model.construct_initial_causal_state(N, len(qf.resolutions) - 1)
+  state = [{k: v.cuda().clone() for k, v in d.items()} for d in state]
+  for t in range(T):
+    tracks, vis = trk.step(video[0, t])
+    gr = model.get_feature_grids(video[:, t:t + 1], False)
+    r = model.estimate_trajectories((256, 256), False, gr, qf, None, 64, causal_context=state,
+                                    get_causal_context=True)
+    state = r['causal_context']
+    assert torch.equal(tracks, r['tracks'][-1]), f'frame {t}'
+    occ, expd = trk.last_logits
+    assert torch.equal(occ, r['occlusion'][-1]) and torch.equal(expd, r['expected_dist'][-1])
+  U.record('c3_graph_tracker', frames=T, equal=1)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
 def test_c4_sharded_equals_single_gpu():
   port = 29500 + os.getpid() % 1000
