@@ -61,6 +61,22 @@ eager = dict(config='causal BootsTAPIR streaming 256x256', frames=a.frames, quer
                       finite=bool(torch.isfinite(tracks).all()))
 print(json.dumps(dict(mode='eager', **eager)))
 
+# per-kernel-class device time of the eager step (CUDA events around every launch)
+import ctypes  # noqa: E402
+from tapnet_b200 import _lib  # noqa: E402
+lib = _lib.load()
+lib.tapir_profile_enable(1)
+for t in range(4):
+  _, _, state = step(t, state)
+buf = ctypes.create_string_buffer(1 << 16)
+if lib.tapir_profile_report(buf, len(buf)) == 0:
+  prof = json.loads(buf.value.decode())
+  tot = sum(v['ms'] for v in prof.values())
+  print('per-frame kernel time by class (ms), total %.3f:' % (tot / 4))
+  for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+    print('  %-26s %7.3f ms  %4d launches  avg %6.1f us' % (k, v['ms'] / 4, v['launches'] // 4, v['ms'] / v['launches'] * 1e3))
+lib.tapir_profile_enable(0)
+
 # CUDA-graph replay of the same per-frame step
 from tapnet_b200 import streaming  # noqa: E402
 
