@@ -183,11 +183,11 @@ __global__ void __launch_bounds__(96) local_corr_kernel(const CorrParams p) {
 //   out: z (fp32) and LN_1(z) * w1 as bf16 planes (the A operand of the `up` GEMM).
 // Non-causal convs zero-pad one frame each side; causal convs look 2 frames back, with
 // the optional context (last 2 frames of y and of h1 from the previous call) standing in for
-// frames -2, -1 (nets.py:149-176).  CTA = one query, `kDwTile` output frames; thread = one of
-// the 512 channels.
-constexpr int kDwTile = 24;
-constexpr int kDwHalo = 4;
-constexpr int kDwRows = kDwTile + kDwHalo;
+// frames -2, -1 (nets.py:149-176).  CTA = QB queries x TT output frames (QB > 1 only for short clips /
+// streaming, so that a CTA always has ~24 rows of work); thread = one of the 512 channels.
+constexpr int kDwTileMax = 24;        // output frames per CTA (per query)
+constexpr int kDwHalo = 4;            // extra layer-normed rows a tile needs (2+2 or 4+0)
+constexpr int kDwRowBudget = 52;      // QB * (2*TT + 4) rows of 2 KB <= 104 KB (2 CTAs per SM)
 
 struct DwParams {
   const float* x;
@@ -196,7 +196,9 @@ struct DwParams {
   long long plane_stride;
   int planes;
   int T;
-  int causal;
+  int N;    // queries
+  int TT;   // output frames per tile
+  int QB;   // queries per CTA (short clips / streaming: several queries share one CTA)
   const float* ln_w;
   const float* w1;
   const float* b1;
@@ -209,61 +211,76 @@ struct DwParams {
   float* ctx2_out;
 };
 
+// One warp: LayerNorm (scale only, eps 1e-5) of a 512-wide row held as 4 float4 per lane.
+__device__ __forceinline__ void ln512(const float4 (&v)[4], const float* __restrict__ w, int lane,
+                                      float4 (&o)[4]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+  const float mean = warp_sum(s) * (1.0f / 512);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) * (1.0f / 512) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 ww = reinterpret_cast<const float4*>(w)[i * 32 + lane];
+    o[i] = make_float4((v[i].x - mean) * rstd * ww.x, (v[i].y - mean) * rstd * ww.y,
+                       (v[i].z - mean) * rstd * ww.z, (v[i].w - mean) * rstd * ww.w);
+  }
+}
+
+template <bool CAUSAL>
 __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
-  extern __shared__ float dw_smem[];  // [kDwRows][512] LN'd rows (recycled for z) + [kDwTile][512] raw x
-  float* xraw = dw_smem + kDwRows * 512;
-  const int n = blockIdx.y;
-  const int t0 = blockIdx.x * kDwTile;
-  const int t1 = min(t0 + kDwTile, p.T);
+  extern __shared__ float dw_smem[];
+  const int TT = p.TT, QB = p.QB, T = p.T;
+  const int RY = TT + kDwHalo;              // layer-normed rows per query
+  float* ybuf = dw_smem;                    // [QB][RY][512]  (rows are recycled for z)
+  float* xraw = dw_smem + QB * RY * 512;    // [QB][TT][512]  raw rows for the skip connection
+  const int t0 = blockIdx.x * TT;
+  const int t1 = min(t0 + TT, T);
+  const int n0 = blockIdx.y * QB;
+  const int nq = min(QB, p.N - n0);
   const int c = threadIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // y rows needed: non-causal t0-2 .. t1+1 ; causal t0-4 .. t1-1.  smem row r <-> frame lo + r.
-  const int lo = p.causal ? t0 - 4 : t0 - 2;
-  const int hi = p.causal ? t1 : t1 + 2;  // exclusive
-  const float* xn = p.x + (long long)n * p.T * 512;
+  // smem row r of a query <-> frame lo + r: non-causal needs t0-2 .. t1+1, causal t0-4 .. t1-1
+  const int lo = CAUSAL ? t0 - 4 : t0 - 2;
+  const int nrow = (CAUSAL ? t1 : t1 + 2) - lo;
 
-  for (int r = warp; r < hi - lo; r += 16) {
-    const int t = lo + r;
-    float* dst = dw_smem + r * 512;
-    if (t >= 0 && t < p.T) {
-      const float4* xr = reinterpret_cast<const float4*>(xn + (long long)t * 512);
-      float4 v[4];
-      float s = 0.f;
+  // ---- phase 1: y = LN(x) * w for every needed row (one warp per row)
+  for (int rq = warp; rq < nq * nrow; rq += 16) {
+    const int q = rq / nrow, r = rq - q * nrow;
+    const int t = lo + r, n = n0 + q;
+    float4* dst = reinterpret_cast<float4*>(ybuf + (q * RY + r) * 512);
+    if (t >= 0 && t < T) {
+      const float4* xr = reinterpret_cast<const float4*>(p.x + ((long long)n * T + t) * 512);
+      float4 v[4], o[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[i] = xr[i * 32 + lane];
-        s += v[i].x + v[i].y + v[i].z + v[i].w;
-      }
-      const float mean = warp_sum(s) * (1.0f / 512);
-      float ss = 0.f;
+      for (int i = 0; i < 4; ++i) v[i] = xr[i * 32 + lane];
+      ln512(v, p.ln_w, lane, o);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-        ss += a * a + b * b + cc * cc + d * d;
-      }
-      const float rstd = 1.0f / sqrtf(warp_sum(ss) * (1.0f / 512) + 1e-5f);
+      for (int i = 0; i < 4; ++i) dst[i * 32 + lane] = o[i];
+      if (t >= t0 && t < t1) {  // the frame loop below must not wait on L2 for the skip input
+        float4* xd = reinterpret_cast<float4*>(xraw + (q * TT + (t - t0)) * 512);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 ww = reinterpret_cast<const float4*>(p.ln_w)[i * 32 + lane];
-        reinterpret_cast<float4*>(dst)[i * 32 + lane] =
-            make_float4((v[i].x - mean) * rstd * ww.x, (v[i].y - mean) * rstd * ww.y,
-                        (v[i].z - mean) * rstd * ww.z, (v[i].w - mean) * rstd * ww.w);
-        // keep the raw row for the skip connection: the frame loop below must not wait on L2
-        if (t >= t0 && t < t1) reinterpret_cast<float4*>(xraw + (t - t0) * 512)[i * 32 + lane] = v[i];
+        for (int i = 0; i < 4; ++i) xd[i * 32 + lane] = v[i];
       }
-    } else if (p.causal && p.ctx1_in != nullptr && t >= -2 && t < 0) {
-      // context frames -2, -1 of the layer-normed input
+    } else if (CAUSAL && p.ctx1_in != nullptr && t >= -2 && t < 0) {
+      // context frames -2, -1 of the layer-normed input (nets.py:149-153)
       const float4* cr = reinterpret_cast<const float4*>(p.ctx1_in + ((long long)n * 2 + (t + 2)) * 512);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i * 32 + lane] = cr[i * 32 + lane];
+      for (int i = 0; i < 4; ++i) dst[i * 32 + lane] = cr[i * 32 + lane];
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(dst)[i * 32 + lane] = make_float4(0, 0, 0, 0);
+      for (int i = 0; i < 4; ++i) dst[i * 32 + lane] = make_float4(0, 0, 0, 0);
     }
   }
   __syncthreads();
 
-  // per-channel weights: 4 multipliers x 3 taps for both convs
+  // ---- phase 2: thread = channel c; both depthwise convs + GELU + group sum + skip
   float w1[4][3], w2[4][3], b1[4], b2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -275,92 +292,85 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
       w2[j][k] = p.w2[(4 * c + j) * 3 + k];
     }
   }
-  auto yv = [&](int t) { return dw_smem[(t - lo) * 512 + c]; };
-  // h1 at frame t (0 outside the sequence; context for frames -2,-1 in causal mode)
-  auto h1 = [&](int t, float (&o)[4]) {
-    if (t >= 0 && t < p.T) {
-      const int base = p.causal ? t - 2 : t - 1;
-      const float a0 = yv(base), a1 = yv(base + 1), a2 = yv(base + 2);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o[j] = gelu_tanh(fmaf(w1[j][2], a2, fmaf(w1[j][1], a1, fmaf(w1[j][0], a0, b1[j]))));
-    } else if (p.causal && p.ctx2_in != nullptr && t >= -2 && t < 0) {
-      const float4 v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + (t + 2)) * 2048 + 4 * c);
-      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    } else {
-      o[0] = o[1] = o[2] = o[3] = 0.f;
-    }
-  };
-
-  // new causal context for the layer-normed input: last two frames of [ctx | y]
-  // (nets.py:153).  Written first: the y rows are recycled for z below.
-  if (p.causal && p.ctx1_out != nullptr) {
-    for (int t = max(t0, p.T - 2); t < t1; ++t) p.ctx1_out[((long long)n * 2 + (t - (p.T - 2))) * 512 + c] = yv(t);
-    if (p.T == 1 && t0 == 0) {
-      // sequence shorter than the context: slot 0 <- old context frame -1
-      p.ctx1_out[((long long)n * 2 + 0) * 512 + c] = (p.ctx1_in != nullptr) ? p.ctx1_in[((long long)n * 2 + 1) * 512 + c] : 0.f;
-      if (p.ctx2_out != nullptr) {
-        float4 v = make_float4(0, 0, 0, 0);
-        if (p.ctx2_in != nullptr) v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + 1) * 2048 + 4 * c);
-        *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + 0) * 2048 + 4 * c) = v;
+  // h1 of frame f = first + j is a function of smem rows j, j+1, j+2 (both modes)
+  const int first = CAUSAL ? t0 - 2 : t0 - 1;
+  for (int q = 0; q < nq; ++q) {
+    const int n = n0 + q;
+    float* yq = ybuf + q * RY * 512 + c;
+    if (CAUSAL && p.ctx1_out != nullptr) {
+      // new context of the layer-normed input: last two frames of [ctx | y] (nets.py:153);
+      // written before the rows are recycled for z
+      for (int t = max(t0, T - 2); t < t1; ++t)
+        p.ctx1_out[((long long)n * 2 + (t - (T - 2))) * 512 + c] = yq[(t - lo) * 512];
+      if (T == 1 && t0 == 0) {  // clip shorter than the context: slot 0 <- old frame -1
+        p.ctx1_out[((long long)n * 2) * 512 + c] =
+            (p.ctx1_in != nullptr) ? p.ctx1_in[((long long)n * 2 + 1) * 512 + c] : 0.f;
+        if (p.ctx2_out != nullptr) {
+          float4 v = make_float4(0, 0, 0, 0);
+          if (p.ctx2_in != nullptr)
+            v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + 1) * 2048 + 4 * c);
+          *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2) * 2048 + 4 * c) = v;
+        }
       }
     }
-  }
-  float ha[4], hb[4], hc[4];  // sliding window of h1 over 3 consecutive frames
-  const int first = p.causal ? t0 - 2 : t0 - 1;
-  h1(first, ha);
-  h1(first + 1, hb);
-  // Column c of the y rows is only ever read by this thread, and after step i the rows
-  // <= i + 2 are dead (both modes), so z[t0 + i] is parked in row i: no per-thread z array.
+    float y0 = yq[0], y1 = yq[512];
+    float ha[4], hb[4], hc[4];
+    auto h1 = [&](int j, float (&o)[4]) {
+      const int f = first + j;
+      const float y2 = yq[(j + 2) * 512];
+      if (f >= 0 && f < T) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          o[m] = gelu_tanh(fmaf(w1[m][2], y2, fmaf(w1[m][1], y1, fmaf(w1[m][0], y0, b1[m]))));
+        if (CAUSAL && p.ctx2_out != nullptr && f >= T - 2)  // last two frames of [ctx | h1] (nets.py:167)
+          *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + (f - (T - 2))) * 2048 + 4 * c) =
+              make_float4(o[0], o[1], o[2], o[3]);
+      } else if (CAUSAL && p.ctx2_in != nullptr && f >= -2 && f < 0) {
+        const float4 v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + (f + 2)) * 2048 + 4 * c);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+      } else {
+        o[0] = o[1] = o[2] = o[3] = 0.f;  // zero padding of the second conv's input
+      }
+      y0 = y1;
+      y1 = y2;
+    };
+    h1(0, ha);
+    h1(1, hb);
+    const float* xq = xraw + q * TT * 512 + c;
 #pragma unroll 2
-  for (int i = 0; i < t1 - t0; ++i) {
-    const int t = t0 + i;
-    h1(first + 2 + i, hc);
-    float acc = xraw[i * 512 + c];
+    for (int i = 0; i < t1 - t0; ++i) {
+      h1(i + 2, hc);
+      float acc = xq[i * 512];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      acc += fmaf(w2[j][2], hc[j], fmaf(w2[j][1], hb[j], fmaf(w2[j][0], ha[j], b2[j])));
-    dw_smem[i * 512 + c] = acc;
-    p.z[((long long)n * p.T + t) * 512 + c] = acc;
-    // new causal context of the hidden activation (last two frames of [ctx | h1], nets.py:167)
-    if (p.causal && p.ctx2_out != nullptr && t >= p.T - 2) {
-      // frame t's own h1 is hc (causal window = frames t-2, t-1, t)
-      *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + (t - (p.T - 2))) * 2048 + 4 * c) =
-          make_float4(hc[0], hc[1], hc[2], hc[3]);
+      for (int m = 0; m < 4; ++m)
+        acc += fmaf(w2[m][2], hc[m], fmaf(w2[m][1], hb[m], fmaf(w2[m][0], ha[m], b2[m])));
+      // rows <= i + 2 of this column are dead by now: park z[t0 + i] in row i
+      yq[i * 512] = acc;
+      p.z[((long long)n * T + t0 + i) * 512 + c] = acc;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { ha[m] = hb[m]; hb[m] = hc[m]; }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { ha[j] = hb[j]; hb[j] = hc[j]; }
   }
   __syncthreads();
-  // LN_1 (scale only) -> bf16 planes
-  for (int r = warp; r < t1 - t0; r += 16) {
-    const float4* zr = reinterpret_cast<const float4*>(dw_smem + r * 512);
-    float4 v[4];
-    float s = 0.f;
+
+  // ---- phase 3: LN_1(z) * w (scale only) -> bf16 planes, the A operand of the `up` GEMM
+  const int ntile = t1 - t0;
+  for (int rq = warp; rq < nq * ntile; rq += 16) {
+    const int q = rq / ntile, i = rq - q * ntile;
+    const float4* zr = reinterpret_cast<const float4*>(ybuf + (q * RY + i) * 512);
+    float4 v[4], o4[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      v[i] = zr[i * 32 + lane];
-      s += v[i].x + v[i].y + v[i].z + v[i].w;
-    }
-    const float mean = warp_sum(s) * (1.0f / 512);
-    float ss = 0.f;
+    for (int k = 0; k < 4; ++k) v[k] = zr[k * 32 + lane];
+    ln512(v, p.ln1_w, lane, o4);
+    const long long orow = (long long)(n0 + q) * T + t0 + i;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-      ss += a * a + b * b + cc * cc + d * d;
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(ss) * (1.0f / 512) + 1e-5f);
-    const long long orow = (long long)n * p.T + t0 + r;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 ww = reinterpret_cast<const float4*>(p.ln1_w)[i * 32 + lane];
-      float o[4] = {(v[i].x - mean) * rstd * ww.x, (v[i].y - mean) * rstd * ww.y,
-                    (v[i].z - mean) * rstd * ww.z, (v[i].w - mean) * rstd * ww.w};
-      for (int q = 0; q < p.planes; ++q) {
+    for (int k = 0; k < 4; ++k) {
+      float o[4] = {o4[k].x, o4[k].y, o4[k].z, o4[k].w};
+      for (int pl = 0; pl < p.planes; ++pl) {
         uint2 pk;
         pk.x = bf16x2_split(o[0], o[1]);
         pk.y = bf16x2_split(o[2], o[3]);
-        *reinterpret_cast<uint2*>(p.planes_out + q * p.plane_stride + orow * 512 + (i * 32 + lane) * 4) = pk;
+        *reinterpret_cast<uint2*>(p.planes_out + pl * p.plane_stride + orow * 512 + (k * 32 + lane) * 4) = pk;
       }
     }
   }
@@ -508,9 +518,10 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     return kWorkspaceTooSmall;
   }
   static bool configured = false;
-  const int dw_smem = (kDwRows + kDwTile) * 512 * (int)sizeof(float);
   if (!configured) {
-    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dw_smem));
+    const int max_smem = kDwRowBudget * 512 * (int)sizeof(float);
+    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured = true;
   }
   {  // nets.py:235 linear
@@ -528,17 +539,27 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     DwParams d;
     d.x = m.xa; d.z = m.xb;
     d.planes_out = m.y; d.plane_stride = rows * 512; d.planes = P;
-    d.T = T; d.causal = io->causal;
+    d.T = T; d.N = n;
+    d.TT = T < kDwTileMax ? T : kDwTileMax;
+    d.QB = kDwRowBudget / (2 * d.TT + kDwHalo);
+    if (d.QB < 1) d.QB = 1;
+    if (d.QB > 8) d.QB = 8;
+    if (d.QB > n) d.QB = n;
     d.ln_w = blk.ln_w; d.w1 = blk.dw1_w; d.b1 = blk.dw1_b; d.w2 = blk.dw2_w; d.b2 = blk.dw2_b;
     d.ln1_w = blk.ln1_w;
     d.ctx1_in = io->ctx1_in ? io->ctx1_in[b] : nullptr;
     d.ctx2_in = io->ctx2_in ? io->ctx2_in[b] : nullptr;
     d.ctx1_out = io->ctx1_out ? io->ctx1_out[b] : nullptr;
     d.ctx2_out = io->ctx2_out ? io->ctx2_out[b] : nullptr;
-    dim3 grid(ceil_div(T, kDwTile), n);
+    dim3 grid(ceil_div(T, d.TT), ceil_div(n, d.QB));
+    const int dw_smem = d.QB * (2 * d.TT + kDwHalo) * 512 * (int)sizeof(float);
     {
       ProfileScope ps("mixer.dw", s, (double)rows * 2048 * 12, (double)rows * 512 * (8 + 2 * P));
-      mixer_dw_kernel<<<grid, 512, dw_smem, s>>>(d);
+      if (io->causal) {
+        mixer_dw_kernel<true><<<grid, 512, dw_smem, s>>>(d);
+      } else {
+        mixer_dw_kernel<false><<<grid, 512, dw_smem, s>>>(d);
+      }
     }
     count_launch();
     TAPIR_LAUNCH_CHECK("mixer_dw_kernel");
