@@ -106,7 +106,15 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
   }
   if (p.residual != nullptr && row_ok) {
     const float* r = p.residual + row * (long long)p.ldr + col0;
-    if (full && (p.ldr & 3) == 0) {
+    if (full && (p.ldr & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t w[8];
+        ptx::ld_global_v8(r + j, w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j + e] += __uint_as_float(w[e]);
+      }
+    } else if (full && (p.ldr & 3) == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 b = *reinterpret_cast<const float4*>(r + j);
@@ -120,7 +128,15 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
   }
   if (p.out_f32 != nullptr && row_ok) {
     float* o = p.out_f32 + row * (long long)p.ldo + col0;
-    if (full && (p.ldo & 3) == 0) {
+    if (full && (p.ldo & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(v[j + e]);
+        ptx::st_global_v8(o + j, w);
+      }
+    } else if (full && (p.ldo & 3) == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -167,7 +183,15 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
     // successive bf16 terms of v: plane q holds bf16(v - sum_{r<q} plane r)
     for (int q = 0; q < p.out_P; ++q) {
       __nv_bfloat16* o = p.out_planes + q * p.out_plane_stride + row * (long long)p.ldp + col0;
-      if (full && (p.ldp & 7) == 0) {
+      if (full && (p.ldp & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 16) {
+          uint32_t w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[e] = bf16x2_split(v[j + 2 * e], v[j + 2 * e + 1]);
+          ptx::st_global_v8(o + j, w);
+        }
+      } else if (full && (p.ldp & 7) == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           uint4 w;

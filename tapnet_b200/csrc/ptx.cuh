@@ -138,6 +138,21 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per request.
+// The GEMM epilogue stores one ROW per thread; with 128-bit stores every request was half a
+// sector and the L2 request rate, not bytes, bounded the K=512 GEMMs.
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* ptr, uint32_t (&r)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                 "=r"(r[7])
+               : "l"(ptr));
+}
+
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are 128 bytes
 // (64 bf16) laid out by TMA with CU_TENSOR_MAP_SWIZZLE_128B: 8-row x 128 B swizzle atoms,
 // consecutive atoms 1024 B apart (SBO); LBO is unused for swizzled K-major (canonical 1).
