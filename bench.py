@@ -136,6 +136,8 @@ def run_ours(args):
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
   if world > 1:
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+      os.environ['NCCL_DEBUG'] = 'WARN'  # keep stdout to the single JSON line
     dist.init_process_group('nccl', device_id=dev)
   lib = _lib.load()
   sd, video_h, queries_h = build_inputs(world)
