@@ -44,6 +44,8 @@ constexpr int kBarrierBytes = 256;
 struct TcParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmBh;     // cluster mode: half-height B box (BLOCK_N/2 rows), multicast to the CTA pair
+  int frames;
   int M, N;
   int num_k_blocks;
   int num_m_tiles, num_n_tiles;
@@ -213,7 +215,10 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
   }
 }
 
-template <int BLOCK_N, int P>
+// CL = 2-CTA cluster: the two CTAs work on vertically adjacent tiles (same columns), each loads
+// half of the shared B tile and multicasts it to both, which removes a quarter of the L2 -> SM
+// operand traffic (the K <= 2048 GEMMs are L2-bound).
+template <int BLOCK_N, int P, bool CL>
 __global__ void __launch_bounds__(num_threads(BLOCK_N), 1)
 gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<BLOCK_N, P>;
@@ -234,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], CL ? 2 : 1);  // cluster: both CTAs' MMAs release the slot
     }
     for (int a = 0; a < kNumAccStages; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
@@ -243,26 +248,36 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tmA);
     ptx::prefetch_tensormap(&p.tmB);
+    if (CL) ptx::prefetch_tensormap(&p.tmBh);
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CL) ptx::cluster_sync(); else __syncthreads();  // barrier inits visible to the peer CTA
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int nkb = p.num_k_blocks;
+  // work items: plain = tiles, cluster = tile pairs (m_tile = 2*pair + rank, same n_tile)
+  const int rank = CL ? (int)ptx::cluster_ctarank() : 0;
+  const int work_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_stride = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_work = (CL ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
+  auto decode = [&](int w, int& m_tile, int& n0) {
+    const int mm = w / p.num_n_tiles;
+    m_tile = CL ? 2 * mm + rank : mm;
+    n0 = (w - mm * p.num_n_tiles) * BLOCK_N;
+  };
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+    for (int w = work_first; w < num_work; w += work_stride) {
+      int m_tile, n0;
+      decode(w, m_tile, n0);
       int frame = 0, y0 = 0, x0 = 0;
       if (p.mode == kGemmConv3x3) {
         const int per_frame = p.tiles_x * p.tiles_y;
@@ -290,9 +305,18 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
             ptx::tma_load_3d(sa + pl * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * kBlockK,
                              m_tile * kBlockM, pl);
         }
+        if (CL) {
+          // my half of the B tile, delivered to both CTAs (the peer sends me the other half)
 #pragma unroll
-        for (int pl = 0; pl < P; ++pl)
-          ptx::tma_load_3d(sb + pl * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, n0, pl);
+          for (int pl = 0; pl < P; ++pl)
+            ptx::tma_load_3d_multicast(sb + pl * Cfg::kBBytes + rank * (Cfg::kBBytes / 2), &p.tmBh,
+                                       &full_bar[stage], kb * kBlockK, n0 + rank * (BLOCK_N / 2), pl,
+                                       (uint16_t)0x3);
+        } else {
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl)
+            ptx::tma_load_3d(sb + pl * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, n0, pl);
+        }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -302,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int w = work_first; w < num_work; w += work_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, p.err, 102);
@@ -328,7 +352,8 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
             }
           }
         }
-        ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+        // smem slot reusable once these MMAs retire (cluster: tell both producers)
+        if (CL) ptx::umma_commit_multicast(&empty_bar[stage], (uint16_t)0x3); else ptx::umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
       ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
@@ -343,11 +368,12 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     const int cbase = ((warp - 2) >> 2) * kChunks;
     float* bias_w = bias_smem + (warp - 2) * (kChunks * 32);  // private to this warp
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int w = work_first; w < num_work; w += work_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m_tile = tile / p.num_n_tiles;
-      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      int m_tile, n0;
+      decode(w, m_tile, n0);
+      const bool tile_valid = m_tile < p.num_m_tiles;  // cluster: odd tile count leaves a ghost
       const int r = q * 32 + lane;
       long long row;
       bool row_ok;
@@ -358,7 +384,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
         const int rr = m_tile % per_frame;
         const int y = (rr / p.tiles_x) * p.tileH + r / p.tileW;
         const int x = (rr % p.tiles_x) * p.tileW + r % p.tileW;
-        row_ok = (y < p.H) && (x < p.W);
+        row_ok = (y < p.H) && (x < p.W) && tile_valid;
         row = ((long long)frame * p.H + y) * p.W + x;
       } else {
         row = (long long)m_tile * kBlockM + r;
@@ -379,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + cbase * 32;
       uint32_t va[32], vb[32];
-      if (p.debug_mode == 1) {
+      if (p.debug_mode == 1 || !tile_valid) {
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -410,7 +436,8 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  // cluster: nobody may exit while the peer can still multicast into its shared memory / barriers
+  if (CL) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -477,23 +504,56 @@ void choose_conv_tile(int H, int W, int* tw, int* th) {
   }
 }
 
+bool use_cluster() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TAPIR_B200_GEMM_CLUSTER");
+    v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int BLOCK_N, int P>
 int launch(const TcParams& p, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_N, P>;
+  static bool configured = false;
+  if (!configured) {
+    TAPIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, P, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    TAPIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, P, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
   const double kl = g.k_logical > 0 ? g.k_logical : g.K;
   const double out_b = (g.out_f32 ? 4.0 : 0.0) + (g.out_planes ? 2.0 * g.out_P : 0.0) + (g.residual ? 4.0 : 0.0);
   const double a_elems = (g.mode == kGemmConv3x3) ? (double)g.M * g.C : (double)g.M * g.K;
   ProfileScope ps(g.tag ? g.tag : "gemm", stream, 2.0 * g.M * g.N * kl,
                   2.0 * P * (a_elems + (double)g.N * g.K) + out_b * g.M * g.N);
-  static bool configured = false;
-  if (!configured) {
-    TAPIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, P>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+  const int sms = num_sms();
+  // pairs of vertically adjacent tiles share their B operand through a 2-CTA cluster
+  const bool cluster = use_cluster() && p.num_m_tiles >= 2 && (sms % 2 == 0);
+  if (cluster) {
+    const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(num_threads(BLOCK_N));
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TAPIR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, P, true>, p));
+  } else {
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = tiles < sms ? tiles : sms;
+    gemm_tc_kernel<BLOCK_N, P, false><<<grid, num_threads(BLOCK_N), Cfg::kSmemBytes, stream>>>(p);
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BLOCK_N, P><<<grid, num_threads(BLOCK_N), Cfg::kSmemBytes, stream>>>(p);
   count_launch();
   TAPIR_LAUNCH_CHECK("gemm_tc_kernel");
   return kOk;
@@ -554,6 +614,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   p.M = g.M;
   p.N = g.N;
   p.num_k_blocks = g.K / kBlockK;
+  p.frames = g.frames;
   p.mode = g.mode;
   p.bias = g.bias;
   p.residual = g.residual;
@@ -605,6 +666,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     cuuint64_t str[2] = {(cuuint64_t)g.ldb * 2, (cuuint64_t)plane * 2};
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)bn, 1};
     TAPIR_RETURN_IF(encode_bf16_map(&p.tmB, g.b, 3, dims, str, box, "B"));
+    cuuint32_t boxh[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(bn / 2), 1};
+    TAPIR_RETURN_IF(encode_bf16_map(&p.tmBh, g.b, 3, dims, str, boxh, "B/half"));
   }
 
 #define TAPIR_TC_CASE(BN, PP) \
