@@ -2,11 +2,11 @@
 //
 // One persistent CTA per SM, 2 + 4*G warps (G = column groups of the epilogue, 16 epilogue warps for
 // BLOCK_N >= 128):
-//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor tiles of A and B planes into a
+//   warp E (one lane)  TMA producer: cp.async.bulk.tensor tiles of A and B planes into a
 //                      multi-stage shared-memory ring (128B-swizzled, K-major)
-//   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16,
+//   warp E+1 (1 lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16,
 //                      fp32 accumulators in TMEM (double buffered: 2 x BLOCK_N columns)
-//   warps 2..          epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row
+//   warps 0..E-1       epilogue: tcgen05.ld the accumulator (one TMEM lane = one output row
 //                      per thread), bias / tanh-GELU / residual, store fp32 and/or bf16 planes
 // Pipelines: full/empty mbarriers between TMA and MMA, tmem_full/tmem_empty between MMA and
 // epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -236,6 +236,11 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Role layout: epilogue warps FIRST (0 .. kEpiWarps-1), then the TMA producer and the MMA issuer.
+  // The warp scheduler favours high warp ids, and a starved single-lane MMA issuer stalls the
+  // tensor pipe: with the issuer as warp 1 every epilogue instruction delayed the main loop.
+  constexpr int kProducerWarp = Cfg::kEpiWarps;
+  constexpr int kMmaWarp = Cfg::kEpiWarps + 1;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
@@ -250,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     ptx::prefetch_tensormap(&p.tmB);
     if (CL) ptx::prefetch_tensormap(&p.tmBh);
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
     ptx::tmem_relinquish();
   }
@@ -271,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     n0 = (w - mm * p.num_n_tiles) * BLOCK_N;
   };
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -320,7 +325,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == kMmaWarp && lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
     int stage = 0;
@@ -358,15 +363,15 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
       }
       ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
     }
-  } else if (warp >= 2) {
+  } else if (warp < Cfg::kEpiWarps) {
     // ------------------------------------------------------------------ epilogue
     // TMEM lane quadrant q = warp % 4 (hardware restriction: a warp may only touch lanes
-    // [32*(warp%4), +32)), column group = (warp - 2) / 4.  TMEM loads are software
+    // [32*(warp%4), +32)), column group = warp / 4.  TMEM loads are software
     // pipelined: chunk i+1 is in flight while chunk i goes through bias / GELU / stores.
     constexpr int kChunks = Cfg::kChunks;
     const int q = warp & 3;
-    const int cbase = ((warp - 2) >> 2) * kChunks;
-    float* bias_w = bias_smem + (warp - 2) * (kChunks * 32);  // private to this warp
+    const int cbase = (warp >> 2) * kChunks;
+    float* bias_w = bias_smem + warp * (kChunks * 32);  // private to this warp
     int it = 0;
     for (int w = work_first; w < num_work; w += work_stride, ++it) {
       const int acc = it & 1;
@@ -438,7 +443,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
   ptx::tc_fence_before();
   // cluster: nobody may exit while the peer can still multicast into its shared memory / barriers
   if (CL) ptx::cluster_sync(); else __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
