@@ -75,6 +75,9 @@ run('resnet conv 64->64 @128', 0, 64, 0, bias=False, conv=(48, 128, 128, 64))
 run('resnet conv 128->128 @64', 0, 128, 0, bias=False, conv=(48, 64, 64, 128))
 run('resnet conv 256->256 @32', 0, 256, 0, bias=False, conv=(48, 32, 32, 256))
 run('linear_in 576->512', 12288, 512, 576)
+run('cost volume c2 (256 q x 48 f)', 256, 49152, 256, P=3, bias=False)
+run('cost volume c4/GPU (512 q x 96 f)', 512, 98304, 256, P=3, bias=False)
+run('cost volume 4096 q x 96 f', 4096, 98304, 256, P=3, bias=False, reps=5)
 run('P=1 up: gelu+planes(1)', 12288, 2048, 512, P=1, gelu=True, planes_out=1, f32_out=False)
 run('P=1 big square', 8192, 8192, 8192, P=1, bias=False, reps=5)
 run('P=2 big square', 8192, 8192, 4096, P=2, bias=False, reps=5)
