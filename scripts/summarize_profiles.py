@@ -80,7 +80,9 @@ for name, rep, which in (('backbone.extra_conv', 'prof_gemm_extra.ncu-rep', None
                          ('mixer.down', 'prof_gemm_mixer.ncu-rep', 1),
                          ('mixer.dw', 'prof_mixer_dw.ncu-rep', None),
                          ('local_corr', 'prof_local_corr.ncu-rep', None),
-                         ('cost_volume.head', 'prof_head.ncu-rep', None)):
+                         ('cost_volume.head', 'prof_head.ncu-rep', None),
+                         ('cost_volume.gemm', 'prof_cost_volume_gemm.ncu-rep', None),
+                         ('backbone.instnorm_apply', 'prof_instnorm_apply.ncu-rep', None)):
   if os.path.exists(os.path.join(OUT, rep)):
     t = traffic_of(rep, which)
     if t:
