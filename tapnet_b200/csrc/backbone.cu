@@ -129,43 +129,62 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __rest
   }
 }
 
+// Finalises the statistics into a per-(frame, channel) affine map y = x * scale + shift
+// (scale = w / sqrt(var + eps), shift = b - mean * scale), so the apply kernel is one FMA.
 __global__ void __launch_bounds__(256) instnorm_finalize_kernel(const double* __restrict__ sums,
-                                                                long long hw, int count,
+                                                                long long hw, int C, int count,
+                                                                const float* __restrict__ w,
+                                                                const float* __restrict__ b,
                                                                 float* __restrict__ mr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
+  const int c = i % C;
   const double mean = sums[2 * i] / (double)hw;
   double var = sums[2 * i + 1] / (double)hw - mean * mean;
   if (var < 0) var = 0;
-  mr[2 * i] = (float)mean;
-  mr[2 * i + 1] = (float)(1.0 / sqrt(var + 1e-5));
+  const double scale = (double)w[c] / sqrt(var + 1e-5);
+  mr[2 * i] = (float)scale;
+  mr[2 * i + 1] = (float)((double)b[c] - mean * scale);
 }
 
+// relu(x * scale + shift) -> bf16 planes.  CTA = one frame x a chunk of pixels; a thread keeps
+// its 4 channels' (scale, shift) in registers and streams pixels, 4 independent loads in flight.
+constexpr int kApplyPixelsPerBlock = 512;
 __global__ void __launch_bounds__(256) instnorm_relu_split_kernel(
-    const float* __restrict__ x, const float* __restrict__ mr, const float* __restrict__ w,
-    const float* __restrict__ b, long long hw, int C, __nv_bfloat16* __restrict__ out,
-    long long plane_stride, int planes, long long total4) {
+    const float* __restrict__ x, const float* __restrict__ mr, long long hw, int C,
+    __nv_bfloat16* __restrict__ out, long long plane_stride, int planes) {
+  const int f = blockIdx.y;
   const int c4n = C / 4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % c4n);
-    const long long pix = i / c4n;
-    const long long f = pix / hw;
-    const float4 v = reinterpret_cast<const float4*>(x)[i];
-    float in[4] = {v.x, v.y, v.z, v.w};
-    float y[4];
+  const int lanes = 256 / c4n;
+  const int g = threadIdx.x % c4n, pl = threadIdx.x / c4n;
+  const float4 s0 = reinterpret_cast<const float4*>(mr + ((long long)f * C + 4 * g) * 2)[0];
+  const float4 s1 = reinterpret_cast<const float4*>(mr + ((long long)f * C + 4 * g) * 2)[1];
+  const float sc[4] = {s0.x, s0.z, s1.x, s1.z}, sh[4] = {s0.y, s0.w, s1.y, s1.w};
+  const long long p0 = (long long)blockIdx.x * kApplyPixelsPerBlock;
+  long long p1 = p0 + kApplyPixelsPerBlock;
+  if (p1 > hw) p1 = hw;
+  const long long base = (long long)f * hw;
+  const float4* xin = reinterpret_cast<const float4*>(x);
+  for (long long p = p0 + pl; p < p1; p += 4 * lanes) {
+    float4 v[4];
+    long long idx[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = g * 4 + e;
-      const float2 st = reinterpret_cast<const float2*>(mr)[f * C + c];
-      const float t = (in[e] - st.x) * st.y * w[c] + b[c];
-      y[e] = fmaxf(t, 0.f);
+    for (int u = 0; u < 4; ++u) {
+      const long long pp = p + (long long)u * lanes;
+      idx[u] = (base + pp) * c4n + g;
+      if (pp < p1) v[u] = xin[idx[u]];
     }
-    for (int q = 0; q < planes; ++q) {
-      uint2 pk;
-      pk.x = bf16x2_split(y[0], y[1]);
-      pk.y = bf16x2_split(y[2], y[3]);
-      reinterpret_cast<uint2*>(out + q * plane_stride)[i] = pk;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p + (long long)u * lanes >= p1) continue;
+      float y[4] = {fmaxf(fmaf(v[u].x, sc[0], sh[0]), 0.f), fmaxf(fmaf(v[u].y, sc[1], sh[1]), 0.f),
+                    fmaxf(fmaf(v[u].z, sc[2], sh[2]), 0.f), fmaxf(fmaf(v[u].w, sc[3], sh[3]), 0.f)};
+      for (int q = 0; q < planes; ++q) {
+        uint2 pk;
+        pk.x = bf16x2_split(y[0], y[1]);
+        pk.y = bf16x2_split(y[2], y[3]);
+        reinterpret_cast<uint2*>(out + q * plane_stride)[idx[u]] = pk;
+      }
     }
   }
 }
@@ -349,8 +368,8 @@ int stem_conv(const float* video, const float* w_packed, int frames, int H, int 
   return kOk;
 }
 
-int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, float* mr,
-                   cudaStream_t s) {
+int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, const float* w,
+                   const float* b, float* mr, cudaStream_t s) {
   TAPIR_CHECK_ARG(C == 64 || C == 128 || C == 256, "instnorm_stats: C=%d unsupported", C);
   ProfileScope ps("backbone.instnorm_stats", s, 0.0, (double)frames * hw * C * 4);
   TAPIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * frames * C, s));
@@ -358,7 +377,7 @@ int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums
   instnorm_stats_kernel<<<grid, 256, 0, s>>>(x, hw, C, sums);
   count_launch();
   TAPIR_LAUNCH_CHECK("instnorm_stats_kernel");
-  instnorm_finalize_kernel<<<ceil_div(frames * C, 256), 256, 0, s>>>(sums, hw, frames * C, mr);
+  instnorm_finalize_kernel<<<ceil_div(frames * C, 256), 256, 0, s>>>(sums, hw, C, frames * C, w, b, mr);
   count_launch();
   TAPIR_LAUNCH_CHECK("instnorm_finalize_kernel");
   return kOk;
@@ -369,20 +388,20 @@ int instnorm_zero(int frames, int C, double* sums, cudaStream_t s) {
   return kOk;
 }
 
-int instnorm_finalize(int frames, long long hw, int C, const double* sums, float* mr, cudaStream_t s) {
-  instnorm_finalize_kernel<<<ceil_div(frames * C, 256), 256, 0, s>>>(sums, hw, frames * C, mr);
+int instnorm_finalize(int frames, long long hw, int C, const double* sums, const float* w,
+                      const float* b, float* mr, cudaStream_t s) {
+  instnorm_finalize_kernel<<<ceil_div(frames * C, 256), 256, 0, s>>>(sums, hw, C, frames * C, w, b, mr);
   count_launch();
   TAPIR_LAUNCH_CHECK("instnorm_finalize_kernel");
   return kOk;
 }
 
-int instnorm_relu_split(const float* x, const float* mr, const float* w, const float* b,
-                        int frames, long long hw, int C, __nv_bfloat16* out, long long plane_stride,
-                        int planes, cudaStream_t s) {
+int instnorm_relu_split(const float* x, const float* mr, int frames, long long hw, int C,
+                        __nv_bfloat16* out, long long plane_stride, int planes, cudaStream_t s) {
   const long long total4 = (long long)frames * hw * C / 4;
   ProfileScope ps("backbone.instnorm_apply", s, 0.0, (double)total4 * (16 + 8 * planes));
-  instnorm_relu_split_kernel<<<grid_for(total4), 256, 0, s>>>(x, mr, w, b, hw, C, out,
-                                                             plane_stride, planes, total4);
+  dim3 grid((unsigned)ceil_div_ll(hw, kApplyPixelsPerBlock), frames);
+  instnorm_relu_split_kernel<<<grid, 256, 0, s>>>(x, mr, hw, C, out, plane_stride, planes);
   count_launch();
   TAPIR_LAUNCH_CHECK("instnorm_relu_split_kernel");
   return kOk;
@@ -529,12 +548,11 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
     float* hbuf = bp.buf[(xi + 3) & 3];
     // bn_0 + relu -> planes
     if (x_stats_ready) {
-      TAPIR_RETURN_IF(instnorm_finalize(frames, (long long)h * wd, b.cin, bp.sums, bp.mr, s));
+      TAPIR_RETURN_IF(instnorm_finalize(frames, (long long)h * wd, b.cin, bp.sums, b.bn0_w, b.bn0_b, bp.mr, s));
     } else {
-      TAPIR_RETURN_IF(instnorm_stats(x, frames, (long long)h * wd, b.cin, bp.sums, bp.mr, s));
+      TAPIR_RETURN_IF(instnorm_stats(x, frames, (long long)h * wd, b.cin, bp.sums, b.bn0_w, b.bn0_b, bp.mr, s));
     }
-    TAPIR_RETURN_IF(instnorm_relu_split(x, bp.mr, b.bn0_w, b.bn0_b, frames, (long long)h * wd,
-                                        b.cin, bp.act, bp.act_plane, P, s));
+    TAPIR_RETURN_IF(instnorm_relu_split(x, bp.mr, frames, (long long)h * wd, b.cin, bp.act, bp.act_plane, P, s));
     const float* shortcut = x;
     if (b.has_proj) {
       GemmArgs g = linear_args(b.proj);
@@ -573,13 +591,12 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
       }
       TAPIR_RETURN_IF(gemm(g, s));
       if (fuse) {
-        TAPIR_RETURN_IF(instnorm_finalize(frames, (long long)oh * ow, b.cout, bp.sums, bp.mr, s));
+        TAPIR_RETURN_IF(instnorm_finalize(frames, (long long)oh * ow, b.cout, bp.sums, b.bn1_w, b.bn1_b, bp.mr, s));
       } else {
-        TAPIR_RETURN_IF(instnorm_stats(hbuf, frames, (long long)oh * ow, b.cout, bp.sums, bp.mr, s));
+        TAPIR_RETURN_IF(instnorm_stats(hbuf, frames, (long long)oh * ow, b.cout, bp.sums, b.bn1_w, b.bn1_b, bp.mr, s));
       }
     }
-    TAPIR_RETURN_IF(instnorm_relu_split(hbuf, bp.mr, b.bn1_w, b.bn1_b, frames, (long long)oh * ow,
-                                        b.cout, bp.act, bp.act_plane, P, s));
+    TAPIR_RETURN_IF(instnorm_relu_split(hbuf, bp.mr, frames, (long long)oh * ow, b.cout, bp.act, bp.act_plane, P, s));
     {
       GemmArgs g = linear_args(b.conv1);
       g.tag = "backbone.conv";
