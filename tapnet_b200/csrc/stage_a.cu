@@ -8,6 +8,8 @@
 // temperature soft-max, arg-max, radius-5 soft arg-max, and the occlusion branch
 // (pad(0,2,0,2), conv3x3 stride 2 16->32 + ReLU, spatial mean, 32->16->2 MLP).
 #include <cfloat>
+#include <cstdlib>
+#include <cstring>
 
 #include "kernels.cuh"
 
@@ -302,6 +304,297 @@ __global__ void __launch_bounds__(256) cost_volume_head_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------ a6 head, tensor-core hid3
+// Same arithmetic as cost_volume_head_kernel, re-organised so that the 16->32 stride-2 conv
+// (80 % of the head FLOPs) runs on the tensor cores as a split-bf16 implicit GEMM per map:
+// M = 256 output pixels, N = 32 channels, K = 9 taps x 16 input channels (one m16n8k16 k-step per
+// tap), three MMAs per product (hi*hi + hi*lo + lo*hi), fp32 accumulation.  ReLU(hid1) is kept as
+// bf16 hi/lo planes in channel-last order (A fragments are plain 32-bit shared loads), and the
+// 16->1 conv is evaluated in exact fp32 from registers as nine per-tap channel dot products
+// (`stap`) that are then gathered - so the soft-argmax path never sees bf16.
+constexpr int kHT = 512;                       // threads per map
+constexpr int kPixW = 9;                       // 32-bit words per pixel: 16 bf16 + 1 pad (bank spread)
+constexpr int kPlaneWords = kOccPlane * kPixW; // 35 x 35 pixels
+constexpr int kTapW = (kG + 2) * (kG + 2);
+
+struct HeadTcSmem {
+  float cv[kTapW];
+  float stap[9 * kTapW];
+  uint32_t occ_hi[kPlaneWords], occ_lo[kPlaneWords];
+  uint32_t w3_hi[9 * 32 * kPixW], w3_lo[9 * 32 * kPixW];  // [tap][co][ci pairs]
+  float w1[16 * 9], b1[16], w2[16 * 9], b3[32];
+  float w4[16 * 32], b4[16], w5[2 * 16], b5[2];
+  float red_f[16 * 4];
+  int red_i[16];
+  float mean32[16][32];
+  float bcast[4];
+  int bcast_i;
+};
+
+template <class SM>
+__device__ __forceinline__ void block_max_first(float v, int idx, SM& sm, int nwarps, float* out_v,
+                                                int* out_i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { sm.red_f[warp] = v; sm.red_i[warp] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bv = sm.red_f[0];
+    int bi = sm.red_i[0];
+    for (int k = 1; k < nwarps; ++k)
+      if (sm.red_f[k] > bv || (sm.red_f[k] == bv && sm.red_i[k] < bi)) { bv = sm.red_f[k]; bi = sm.red_i[k]; }
+    sm.bcast[0] = bv;
+    sm.bcast_i = bi;
+  }
+  __syncthreads();
+  *out_v = sm.bcast[0];
+  *out_i = sm.bcast_i;
+}
+
+template <class SM>
+__device__ __forceinline__ void block_sum3(float a, float b, float c, SM& sm, int nwarps, float* oa,
+                                           float* ob, float* oc) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { sm.red_f[warp * 4] = a; sm.red_f[warp * 4 + 1] = b; sm.red_f[warp * 4 + 2] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0, y = 0, z = 0;
+    for (int k = 0; k < nwarps; ++k) { x += sm.red_f[k * 4]; y += sm.red_f[k * 4 + 1]; z += sm.red_f[k * 4 + 2]; }
+    sm.bcast[0] = x; sm.bcast[1] = y; sm.bcast[2] = z;
+  }
+  __syncthreads();
+  *oa = sm.bcast[0]; *ob = sm.bcast[1]; *oc = sm.bcast[2];
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
+    const tapir_head_weights w, const float* __restrict__ cost_volume, int T,
+    const float* __restrict__ query_tyx, float temperature, int init_h, int init_w,
+    float* __restrict__ points, float* __restrict__ occ_out, float* __restrict__ expd_out,
+    int* __restrict__ argmax_out) {
+  extern __shared__ __align__(16) uint8_t head_tc_smem_raw[];
+  HeadTcSmem& sm = *reinterpret_cast<HeadTcSmem*>(head_tc_smem_raw);
+  const int t = blockIdx.x, n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const float* cv = cost_volume + ((long long)n * T + t) * (kG * kG);
+
+  // ---- phase A: zero halos, stage weights (hid3 weights as bf16 hi/lo planes [tap][co][ci])
+  for (int i = tid; i < kTapW; i += kHT) sm.cv[i] = 0.f;
+  for (int i = tid; i < 9 * kTapW; i += kHT) sm.stap[i] = 0.f;
+  for (int i = tid; i < kPlaneWords; i += kHT) { sm.occ_hi[i] = 0u; sm.occ_lo[i] = 0u; }
+  for (int i = tid; i < 9 * 32 * 8; i += kHT) {
+    const int cp = i & 7, co = (i >> 3) & 31, tap = i >> 8;
+    float v0 = w.hid3_w[(co * 16 + 2 * cp) * 9 + tap], v1 = w.hid3_w[(co * 16 + 2 * cp + 1) * 9 + tap];
+    const uint32_t hi = bf16x2_split(v0, v1);
+    const uint32_t lo = bf16x2_split(v0, v1);
+    sm.w3_hi[(tap * 32 + co) * kPixW + cp] = hi;
+    sm.w3_lo[(tap * 32 + co) * kPixW + cp] = lo;
+  }
+  if (tid < 144) { sm.w1[tid] = w.hid1_w[tid]; sm.w2[tid] = w.hid2_w[tid]; }
+  if (tid < 16) { sm.b1[tid] = w.hid1_b[tid]; sm.b4[tid] = w.hid4_b[tid]; }
+  if (tid < 32) { sm.b3[tid] = w.hid3_b[tid]; sm.w5[tid] = w.occ_w[tid]; }
+  if (tid < 2) sm.b5[tid] = w.occ_b[tid];
+  sm.w4[tid] = w.hid4_w[tid];
+  __syncthreads();
+  for (int i = tid; i < kG * kG; i += kHT) sm.cv[((i >> 5) + 1) * (kG + 2) + (i & 31) + 1] = cv[i];
+  __syncthreads();
+
+  // ---- phase B: hid1 (conv3x3 1->16, padding 1, ReLU) for 2 adjacent pixels of one row; the
+  // 16 channel values go to the bf16 planes and into the nine per-tap dot products of hid2
+  const int y = tid >> 4, x0 = (tid & 15) * 2;
+  {
+    float win[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) win[r][c] = sm.cv[(y + r) * (kG + 2) + x0 + c];
+    float st[2][9];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) st[p][k] = 0.f;
+    const int pix0 = (y + 1) * kOccW + (x0 + 1);
+#pragma unroll 2
+    for (int cp = 0; cp < 8; ++cp) {
+      float o[2][2];  // [pixel][channel of the pair]
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int co = 2 * cp + e;
+        float a0 = sm.b1[co], a1 = a0;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float wv = sm.w1[co * 9 + ky * 3 + kx];
+            a0 = fmaf(win[ky][kx], wv, a0);
+            a1 = fmaf(win[ky][kx + 1], wv, a1);
+          }
+        o[0][e] = fmaxf(a0, 0.f);
+        o[1][e] = fmaxf(a1, 0.f);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float w2v = sm.w2[co * 9 + k];
+          st[0][k] = fmaf(o[0][e], w2v, st[0][k]);
+          st[1][k] = fmaf(o[1][e], w2v, st[1][k]);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        float v0 = o[p][0], v1 = o[p][1];
+        const uint32_t hi = bf16x2_split(v0, v1);
+        const uint32_t lo = bf16x2_split(v0, v1);
+        sm.occ_hi[(pix0 + p) * kPixW + cp] = hi;
+        sm.occ_lo[(pix0 + p) * kPixW + cp] = lo;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) sm.stap[k * kTapW + (y + 1) * (kG + 2) + (x0 + p + 1)] = st[p][k];
+  }
+  __syncthreads();
+
+  // ---- phase C: hid2 = b2 + sum over taps of the neighbours' per-tap dot products; softmax,
+  // arg-max of the probabilities (lowest index on ties), radius-5 soft arg-max (utils.py:116-150)
+  float heat[2];
+  {
+    const float b2 = w.hid2_b[0];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      float a = b2;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+          a += sm.stap[(ky * 3 + kx) * kTapW + (y + ky) * (kG + 2) + (x0 + p + kx)];
+      heat[p] = a * temperature;
+    }
+  }
+  int dummy;
+  float gmax;
+  block_max_first(fmaxf(heat[0], heat[1]), 0, sm, 16, &gmax, &dummy);
+  float e[2];
+  e[0] = expf(heat[0] - gmax);
+  e[1] = expf(heat[1] - gmax);
+  float gsum, u1, u2;
+  block_sum3(e[0] + e[1], 0.f, 0.f, sm, 16, &gsum, &u1, &u2);
+  float prob[2];
+  float pbest = -1.f;
+  int ibest = 0;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    prob[p] = e[p] / gsum;
+    if (prob[p] > pbest) { pbest = prob[p]; ibest = y * kG + x0 + p; }
+  }
+  float pm;
+  int am;
+  block_max_first(pbest, ibest, sm, 16, &pm, &am);
+  const float cx = (float)(am & 31) + 0.5f, cy = (float)(am >> 5) + 0.5f;
+  float sx = 0.f, sy = 0.f, sw = 0.f;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const float px = (float)(x0 + p) + 0.5f, py = (float)y + 0.5f;
+    const float dx = px - cx, dy = py - cy;
+    if (dx * dx + dy * dy < 25.f) { sx += px * prob[p]; sy += py * prob[p]; sw += prob[p]; }
+  }
+  float tx, ty, tw;
+  block_sum3(sx, sy, sw, sm, 16, &tx, &ty, &tw);
+
+  // ---- phase D: hid3 (pad(0,2,0,2), conv3x3 stride 2, 16->32) on the tensor cores.
+  // warp = output row oy (16 output pixels = one m16 tile), 4 n8 tiles, one k16 step per tap.
+  {
+    const int oy = warp, g = lane >> 2, tq = lane & 3;
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const int pa = ((2 * oy + ky + 1) * kOccW + (2 * g + kx + 1)) * kPixW;  // output pixel ox = g
+      const int pb = pa + 16 * kPixW;                                         // ox = g + 8
+      uint32_t ah[4], al[4];
+      ah[0] = sm.occ_hi[pa + tq]; ah[1] = sm.occ_hi[pb + tq];
+      ah[2] = sm.occ_hi[pa + tq + 4]; ah[3] = sm.occ_hi[pb + tq + 4];
+      al[0] = sm.occ_lo[pa + tq]; al[1] = sm.occ_lo[pb + tq];
+      al[2] = sm.occ_lo[pa + tq + 4]; al[3] = sm.occ_lo[pb + tq + 4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int wb = (tap * 32 + nt * 8 + g) * kPixW + tq;
+        uint32_t bh[2] = {sm.w3_hi[wb], sm.w3_hi[wb + 4]};
+        uint32_t bl[2] = {sm.w3_lo[wb], sm.w3_lo[wb + 4]};
+        mma_bf16_16816(acc[nt], al, bh);
+        mma_bf16_16816(acc[nt], ah, bl);
+        mma_bf16_16816(acc[nt], ah, bh);
+      }
+    }
+    // bias + ReLU, then the spatial sum of this warp's 16 pixels per channel: a thread owns
+    // rows g, g+8 and channels nt*8 + 2*tq + {0,1}
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const float b = sm.b3[nt * 8 + 2 * tq + e2];
+        float v = fmaxf(acc[nt][e2] + b, 0.f) + fmaxf(acc[nt][2 + e2] + b, 0.f);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0) sm.mean32[warp][nt * 8 + 2 * tq + e2] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float m = 0.f;
+    for (int k = 0; k < 16; ++k) m += sm.mean32[k][tid];
+    sm.mean32[0][tid] = m * (1.0f / 256.0f);
+  }
+  __syncthreads();
+  if (tid < 16) {
+    float a = sm.b4[tid];
+    for (int k = 0; k < 32; ++k) a = fmaf(sm.mean32[0][k], sm.w4[tid * 32 + k], a);
+    sm.mean32[1][tid] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float a = sm.b5[tid];
+    for (int k = 0; k < 16; ++k) a = fmaf(sm.mean32[1][k], sm.w5[tid * 16 + k], a);
+    const long long o = (long long)n * T + t;
+    if (tid == 0) occ_out[o] = a; else expd_out[o] = a;
+  }
+  if (tid == 0) {
+    const long long o = (long long)n * T + t;
+    const float den = fmaxf(tw, 1e-12f);
+    float px = __fdiv_rn(__fmul_rn(tx / den, (float)init_w), (float)kG);
+    float py = __fdiv_rn(__fmul_rn(ty / den, (float)init_h), (float)kG);
+    if (query_tyx != nullptr) {
+      const float qf = rintf(query_tyx[n * 3 + 0]);
+      if (qf == (float)t) { px = query_tyx[n * 3 + 2]; py = query_tyx[n * 3 + 1]; }
+    }
+    points[o * 2 + 0] = px;
+    points[o * 2 + 1] = py;
+    if (argmax_out != nullptr) argmax_out[o] = am;
+  }
+}
+
 }  // namespace
 
 int sample_query_features(const float* grid, int T, int gh, int gw, int C, const float* query_tyx,
@@ -318,18 +611,27 @@ int sample_query_features(const float* grid, int T, int gh, int gw, int C, const
 int cost_volume_head(const tapir_head_weights* w, const float* cost_volume, int N, int T,
                      const float* query_tyx, float temperature, int init_h, int init_w,
                      float* points, float* occ, float* expd, int* argmax, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
+  static int use_simt = -1;
+  if (use_simt < 0) {
+    const char* e = getenv("TAPIR_B200_HEAD");
+    use_simt = (e != nullptr && strcmp(e, "simt") == 0) ? 1 : 0;
     TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(HeadSmem)));
-    configured = true;
+    TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(HeadTcSmem)));
   }
   TAPIR_CHECK_ARG(N <= 65535, "cost_volume_head: at most 65535 queries per call (got %d)", N);
   // head = 2,950,208 FLOP per (n,t); 4 KB map in, 16 B out
   ProfileScope ps("cost_volume.head", s, 2950208.0 * N * T, (double)N * T * (4096 + 16));
   dim3 grid(T, N);
-  cost_volume_head_kernel<<<grid, 256, sizeof(HeadSmem), s>>>(*w, cost_volume, T, query_tyx, temperature,
-                                                             init_h, init_w, points, occ, expd, argmax);
+  if (use_simt) {
+    cost_volume_head_kernel<<<grid, 256, sizeof(HeadSmem), s>>>(*w, cost_volume, T, query_tyx, temperature,
+                                                               init_h, init_w, points, occ, expd, argmax);
+  } else {
+    cost_volume_head_tc_kernel<<<grid, kHT, sizeof(HeadTcSmem), s>>>(*w, cost_volume, T, query_tyx,
+                                                                    temperature, init_h, init_w, points,
+                                                                    occ, expd, argmax);
+  }
   count_launch();
   TAPIR_LAUNCH_CHECK("cost_volume_head_kernel");
   return kOk;
