@@ -384,18 +384,17 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 }
 
 __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
-    const tapir_head_weights w, const float* __restrict__ cost_volume, int T,
+    const tapir_head_weights w, const float* __restrict__ cost_volume, int T, int num_maps,
     const float* __restrict__ query_tyx, float temperature, int init_h, int init_w,
     float* __restrict__ points, float* __restrict__ occ_out, float* __restrict__ expd_out,
     int* __restrict__ argmax_out) {
   extern __shared__ __align__(16) uint8_t head_tc_smem_raw[];
   HeadTcSmem& sm = *reinterpret_cast<HeadTcSmem*>(head_tc_smem_raw);
-  const int t = blockIdx.x, n = blockIdx.y;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const float* cv = cost_volume + ((long long)n * T + t) * (kG * kG);
 
-  // ---- phase A: zero halos, stage weights (hid3 weights as bf16 hi/lo planes [tap][co][ci])
+  // ---- phase A (once per persistent CTA): zero halos, stage weights (hid3 weights as bf16
+  // hi/lo planes [tap][co][ci]); the interiors are fully rewritten for every map
   for (int i = tid; i < kTapW; i += kHT) sm.cv[i] = 0.f;
   for (int i = tid; i < 9 * kTapW; i += kHT) sm.stap[i] = 0.f;
   for (int i = tid; i < kPlaneWords; i += kHT) { sm.occ_hi[i] = 0u; sm.occ_lo[i] = 0u; }
@@ -412,7 +411,11 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
   if (tid < 32) { sm.b3[tid] = w.hid3_b[tid]; sm.w5[tid] = w.occ_w[tid]; }
   if (tid < 2) sm.b5[tid] = w.occ_b[tid];
   sm.w4[tid] = w.hid4_w[tid];
-  __syncthreads();
+
+  for (int map = blockIdx.x; map < num_maps; map += gridDim.x) {
+  const int n = map / T, t = map - n * T;
+  const float* cv = cost_volume + (long long)map * (kG * kG);
+  __syncthreads();  // previous map fully consumed (planes, stap, mean32) / phase A visible
   for (int i = tid; i < kG * kG; i += kHT) sm.cv[((i >> 5) + 1) * (kG + 2) + (i & 31) + 1] = cv[i];
   __syncthreads();
 
@@ -593,6 +596,7 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
     points[o * 2 + 1] = py;
     if (argmax_out != nullptr) argmax_out[o] = am;
   }
+  }  // map loop
 }
 
 }  // namespace
@@ -628,7 +632,9 @@ int cost_volume_head(const tapir_head_weights* w, const float* cost_volume, int 
     cost_volume_head_kernel<<<grid, 256, sizeof(HeadSmem), s>>>(*w, cost_volume, T, query_tyx, temperature,
                                                                init_h, init_w, points, occ, expd, argmax);
   } else {
-    cost_volume_head_tc_kernel<<<grid, kHT, sizeof(HeadTcSmem), s>>>(*w, cost_volume, T, query_tyx,
+    const int maps = N * T;
+    const int ctas = maps < num_sms() ? maps : num_sms();
+    cost_volume_head_tc_kernel<<<ctas, kHT, sizeof(HeadTcSmem), s>>>(*w, cost_volume, T, maps, query_tyx,
                                                                     temperature, init_h, init_w, points,
                                                                     occ, expd, argmax);
   }
