@@ -412,11 +412,22 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
   if (tid < 2) sm.b5[tid] = w.occ_b[tid];
   sm.w4[tid] = w.hid4_w[tid];
 
+  // the next map's 4 KB are fetched into registers (2 floats per thread) while the current map
+  // is processed, so the L2/HBM latency is not exposed between maps
+  float2 pre = make_float2(0.f, 0.f);
+  if ((int)blockIdx.x < num_maps)
+    pre = reinterpret_cast<const float2*>(cost_volume + (long long)blockIdx.x * (kG * kG))[tid];
   for (int map = blockIdx.x; map < num_maps; map += gridDim.x) {
   const int n = map / T, t = map - n * T;
-  const float* cv = cost_volume + (long long)map * (kG * kG);
   __syncthreads();  // previous map fully consumed (planes, stap, mean32) / phase A visible
-  for (int i = tid; i < kG * kG; i += kHT) sm.cv[((i >> 5) + 1) * (kG + 2) + (i & 31) + 1] = cv[i];
+  {
+    const int i = 2 * tid;  // pixels i, i+1 of the 32x32 map (same row)
+    float* d = sm.cv + ((i >> 5) + 1) * (kG + 2) + (i & 31) + 1;
+    d[0] = pre.x;
+    d[1] = pre.y;
+    const int nxt = map + gridDim.x;
+    if (nxt < num_maps) pre = reinterpret_cast<const float2*>(cost_volume + (long long)nxt * (kG * kG))[tid];
+  }
   __syncthreads();
 
   // ---- phase B: hid1 (conv3x3 1->16, padding 1, ReLU) for 2 adjacent pixels of one row; the
