@@ -468,12 +468,15 @@ int bilinear_resize(const float* src, int frames, int H, int W, int C, float* ds
 
 namespace {
 
+constexpr size_t kBackboneSplitKBytes = 40u << 20;
+
 struct BackbonePlan {
   float* buf[4];            // fp32 activation buffers (ping-pong / shortcut / conv_0 output)
   __nv_bfloat16* act;       // normalised activation planes
   __nv_bfloat16* col;       // im2col planes (stride-2 layers) / ExtraConvs hidden planes
   double* sums;             // instance-norm statistics (fp64 sum, sum of squares)
-  float* mr;                // finalised (mean, rstd) per (frame, channel)
+  float* mr;                // finalised (scale, shift) per (frame, channel)
+  float* splitk;            // split-K scratch for single-frame (streaming) calls
   long long act_plane, col_plane;
 };
 
@@ -491,6 +494,7 @@ size_t plan_backbone(Arena& a, int frames, int H, int W, int extra, int planes, 
   bp->col = a.take<__nv_bfloat16>(col_elems * planes);
   bp->sums = a.take<double>((size_t)frames * 256 * 2);
   bp->mr = a.take<float>((size_t)frames * 256 * 2);
+  bp->splitk = a.take<float>(kBackboneSplitKBytes / sizeof(float));
   return a.off;
 }
 
@@ -631,6 +635,7 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
     {
       GemmArgs g = linear_args(b.conv);
       g.tag = "backbone.extra_conv";
+      g.splitk_ws = bp.splitk; g.splitk_ws_bytes = kBackboneSplitKBytes;
       g.mode = kGemmConv3x3;
       g.M = (int)m;
       g.a = bp.act; g.a_plane_stride = bp.act_plane;
@@ -642,6 +647,7 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
     {
       GemmArgs g = linear_args(b.conv1);
       g.tag = "backbone.extra_conv";
+      g.splitk_ws = bp.splitk; g.splitk_ws_bytes = kBackboneSplitKBytes;
       g.mode = kGemmConv3x3;
       g.M = (int)m;
       g.a = bp.col; g.a_plane_stride = bp.col_plane;

@@ -44,6 +44,8 @@ struct GemmArgs {
   int out_P = 0;
   double* stats = nullptr;  // optional fused per-(frame, column) sum / sum-of-squares (fp64)
   int rows_per_frame = 0;   // plain mode: rows per frame (multiple of 128); conv: implied
+  float* splitk_ws = nullptr;  // optional scratch enabling split-K for under-filled problems
+  size_t splitk_ws_bytes = 0;
   int k_logical = 0;        // un-padded K for FLOP accounting (0 = K)
   const char* tag = nullptr;  // profiling class name
 };

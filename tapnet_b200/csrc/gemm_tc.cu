@@ -63,6 +63,8 @@ struct TcParams {
   int out_P;
   double* stats;        // optional [frames][N][2] column (sum, sum of squares) accumulators
   int rows_per_frame;   // rows of one frame (plain mode; conv tiles never straddle frames)
+  int split_k;          // >1: K is split over `split_k` work items; raw fp32 partials go to out_f32
+  long long split_stride;  // elements between partial buffers (M * ldo)
   int* err;
   int debug_mode;       // bring-up only: 1 = epilogue skips TMEM loads and stores
 };
@@ -90,7 +92,7 @@ struct TcCfg {
 __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row, int col0,
                                                 const uint32_t (&acc)[32],
                                                 const float* __restrict__ bias_s, bool row_ok,
-                                                int frame, int lane) {
+                                                int frame, int lane, long long out_off) {
   const bool full = (col0 + 32 <= p.N);
   if (p.debug_mode == 3) row &= 127;  // bring-up: all tiles store to the same rows (L2-resident)
   float v[32];
@@ -130,7 +132,7 @@ __device__ __forceinline__ void store_row_chunk(const TcParams& p, long long row
     }
   }
   if (p.out_f32 != nullptr && row_ok) {
-    float* o = p.out_f32 + row * (long long)p.ldo + col0;
+    float* o = p.out_f32 + out_off + row * (long long)p.ldo + col0;
     if (full && (p.ldo & 7) == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -270,11 +272,18 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
   const int rank = CL ? (int)ptx::cluster_ctarank() : 0;
   const int work_first = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int work_stride = CL ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int num_work = (CL ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
-  auto decode = [&](int w, int& m_tile, int& n0) {
-    const int mm = w / p.num_n_tiles;
+  // split-K (small problems that cannot fill the GPU): work item = (tile, k-slice)
+  const int S = p.split_k;
+  const int num_work = (CL ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles * S;
+  auto decode = [&](int w, int& m_tile, int& n0, int& kb0, int& kb1) {
+    const int split = w % S;
+    const int tile = w / S;
+    const int mm = tile / p.num_n_tiles;
     m_tile = CL ? 2 * mm + rank : mm;
-    n0 = (w - mm * p.num_n_tiles) * BLOCK_N;
+    n0 = (tile - mm * p.num_n_tiles) * BLOCK_N;
+    kb0 = (int)((long long)nkb * split / S);
+    kb1 = (int)((long long)nkb * (split + 1) / S);
+    return split;
   };
 
   if (warp == kProducerWarp && lane == 0) {
@@ -282,8 +291,8 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     int stage = 0;
     uint32_t phase = 0;
     for (int w = work_first; w < num_work; w += work_stride) {
-      int m_tile, n0;
-      decode(w, m_tile, n0);
+      int m_tile, n0, kb0, kb1;
+      decode(w, m_tile, n0, kb0, kb1);
       int frame = 0, y0 = 0, x0 = 0;
       if (p.mode == kGemmConv3x3) {
         const int per_frame = p.tiles_x * p.tiles_y;
@@ -292,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
         y0 = (r / p.tiles_x) * p.tileH;
         x0 = (r % p.tiles_x) * p.tileW;
       }
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 101);
         ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -338,12 +347,14 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, p.err, 102);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < nkb; ++kb) {
+      int m_tile_unused, n0_unused, kb0, kb1;
+      decode(w, m_tile_unused, n0_unused, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase, p.err, 103);
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
         const uint32_t sb = sa + P * Cfg::kABytes;
-        uint32_t accumulate = (kb > 0) ? 1u : 0u;
+        uint32_t accumulate = (kb > kb0) ? 1u : 0u;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
 #pragma unroll
@@ -377,8 +388,8 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
     for (int w = work_first; w < num_work; w += work_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      int m_tile, n0;
-      decode(w, m_tile, n0);
+      int m_tile, n0, kb0, kb1;
+      const int split = decode(w, m_tile, n0, kb0, kb1);
       const bool tile_valid = m_tile < p.num_m_tiles;  // cluster: odd tile count leaves a ghost
       const int r = q * 32 + lane;
       long long row;
@@ -424,14 +435,14 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
         if (col0 < p.N) {
           ptx::tmem_ld_wait();
           if (i + 1 < kChunks && col0 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 1) * 32, vb);
-          if (row_ok || p.stats != nullptr) store_row_chunk(p, row, col0, va, bias_w + i * 32, row_ok, frame, lane);
+          if (row_ok || p.stats != nullptr) store_row_chunk(p, row, col0, va, bias_w + i * 32, row_ok, frame, lane, split * p.split_stride);
         }
         if (i + 1 < kChunks) {
           const int col1 = col0 + 32;
           if (col1 < p.N) {
             ptx::tmem_ld_wait();
             if (i + 2 < kChunks && col1 + 32 < p.N) ptx::tmem_ld_32x32(taddr + (i + 2) * 32, va);
-            if (row_ok || p.stats != nullptr) store_row_chunk(p, row, col1, vb, bias_w + (i + 1) * 32, row_ok, frame, lane);
+            if (row_ok || p.stats != nullptr) store_row_chunk(p, row, col1, vb, bias_w + (i + 1) * 32, row_ok, frame, lane, split * p.split_stride);
           }
         }
       }
@@ -447,6 +458,41 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
   if (warp == kMmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// Second pass of a split-K GEMM: sums the k-slice partials in a fixed order (deterministic) and
+// applies the epilogue (bias, GELU, residual, fp32 / bf16-plane outputs).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int S,
+                                                            long long split_stride, int ldw,
+                                                            const TcParams p) {
+  const int groups = (p.N + 3) / 4;
+  const long long total = (long long)p.M * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / groups;
+    const int col = (int)(i - row * groups) * 4;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < S; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(part + s * split_stride + row * ldw + col);
+      x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (col + e >= p.N) continue;
+      float v = x[e];
+      if (p.bias != nullptr) v += p.bias[col + e];
+      if (p.act == 1) v = gelu_tanh(v);
+      if (p.residual != nullptr) v += p.residual[row * p.ldr + col + e];
+      if (p.out_f32 != nullptr) p.out_f32[row * p.ldo + col + e] = v;
+      if (p.out_planes != nullptr) {
+        for (int q = 0; q < p.out_P; ++q) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          v -= __bfloat162float(h);
+          p.out_planes[q * p.out_plane_stride + row * p.ldp + col + e] = h;
+        }
+      }
+    }
   }
 }
 
@@ -677,6 +723,40 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     TAPIR_RETURN_IF(encode_bf16_map(&p.tmB, g.b, 3, dims, str, box, "B"));
     cuuint32_t boxh[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(bn / 2), 1};
     TAPIR_RETURN_IF(encode_bf16_map(&p.tmBh, g.b, 3, dims, str, boxh, "B/half"));
+  }
+
+  // split-K for problems that cannot fill the GPU (streaming: T = 1): deterministic two-pass
+  p.split_k = 1;
+  p.split_stride = 0;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int sms = num_sms();
+  if (g.splitk_ws != nullptr && g.stats == nullptr && tiles * 2 <= sms && p.num_k_blocks >= 8) {
+    int S = sms / tiles;
+    if (S > 8) S = 8;
+    if (S > p.num_k_blocks / 4) S = p.num_k_blocks / 4;
+    const int ldw = (g.N + 7) / 8 * 8;
+    while (S > 1 && (size_t)S * g.M * ldw * sizeof(float) > g.splitk_ws_bytes) --S;
+    if (S > 1) {
+      TcParams q = p;  // first pass: raw partial sums
+      q.split_k = S;
+      q.split_stride = (long long)g.M * ldw;
+      q.bias = nullptr; q.residual = nullptr; q.act = 0; q.out_planes = nullptr; q.stats = nullptr;
+      q.out_f32 = g.splitk_ws; q.ldo = ldw;
+      int rc = kUnsupported;
+#define TAPIR_TC_SPLIT(BN, PP) \
+      if (bn == BN && P == PP) rc = launch<BN, PP>(q, g, stream);
+      TAPIR_TC_SPLIT(64, 1) TAPIR_TC_SPLIT(64, 2) TAPIR_TC_SPLIT(64, 3)
+      TAPIR_TC_SPLIT(128, 1) TAPIR_TC_SPLIT(128, 2) TAPIR_TC_SPLIT(128, 3)
+#undef TAPIR_TC_SPLIT
+      TAPIR_RETURN_IF(rc);
+      const long long total = (long long)g.M * ((g.N + 3) / 4);
+      long long blocks = (total + 255) / 256;
+      if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+      splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g.splitk_ws, S, q.split_stride, ldw, p);
+      count_launch();
+      TAPIR_LAUNCH_CHECK("splitk_reduce_kernel");
+      return kOk;
+    }
   }
 
 #define TAPIR_TC_CASE(BN, PP) \

@@ -472,12 +472,15 @@ struct MixerPlan {
   float* xb;
   __nv_bfloat16* y;  // [P][rows][512]
   __nv_bfloat16* h;  // [P][rows][2048]
+  float* splitk;     // split-K scratch (streaming / tiny batches)
 };
+constexpr size_t kSplitKBytes = 40u << 20;
 size_t plan_mixer(Arena& a, long long rows, int planes, MixerPlan* m) {
   m->xa = a.take<float>((size_t)rows * 512);
   m->xb = a.take<float>((size_t)rows * 512);
   m->y = a.take<__nv_bfloat16>((size_t)rows * 512 * planes);
   m->h = a.take<__nv_bfloat16>((size_t)rows * 2048 * planes);
+  m->splitk = a.take<float>(kSplitKBytes / sizeof(float));
   return a.off;
 }
 GemmArgs lin(const tapir_linear& l) {
@@ -527,6 +530,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
   {  // nets.py:235 linear
     GemmArgs g = lin(w->linear);
     g.tag = "mixer.linear_in";
+    g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes;
     g.M = (int)rows;
     g.a = static_cast<const __nv_bfloat16*>(io->x_planes);
     g.lda = io->ldx;
@@ -566,6 +570,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     {
       GemmArgs g = lin(blk.up);
       g.tag = "mixer.up";
+      g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes;
       g.M = (int)rows;
       g.a = m.y; g.lda = 512; g.a_plane_stride = rows * 512;
       g.act = 1;
@@ -575,6 +580,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     {
       GemmArgs g = lin(blk.down);
       g.tag = "mixer.down";
+      g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes;
       g.M = (int)rows;
       g.a = m.h; g.lda = 2048; g.a_plane_stride = rows * 2048;
       g.residual = m.xb; g.ldr = 512;
@@ -586,6 +592,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
   {
     GemmArgs g = lin(w->linear_1);
     g.tag = "mixer.linear_out";
+    g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes;
     g.M = (int)rows;
     g.a = m.y; g.lda = 512; g.a_plane_stride = rows * 512;
     g.out_f32 = io->out; g.ldo = io->ldo;

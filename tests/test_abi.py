@@ -35,7 +35,8 @@ def test_version_and_error_string():
 def test_workspace_queries_need_no_gpu():
   lib = _lib.load()
   assert lib.tapir_backbone_workspace_bytes(48, 256, 256, 1, 2) > 1 << 30
-  assert lib.tapir_mixer_workspace_bytes(12288, 2) == 12288 * (512 * 4 * 2 + 512 * 2 * 2 + 2048 * 2 * 2) + 256
+  base = 12288 * (512 * 4 * 2 + 512 * 2 * 2 + 2048 * 2 * 2)
+  assert base + (40 << 20) <= lib.tapir_mixer_workspace_bytes(12288, 2) <= base + (41 << 20)
   assert lib.tapir_cost_volume_workspace_bytes(256, 48, 32, 32, 256) > 256 * 48 * 1024 * 4
 
 
