@@ -730,7 +730,12 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   p.split_stride = 0;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = num_sms();
-  if (g.splitk_ws != nullptr && g.stats == nullptr && tiles * 2 <= sms && p.num_k_blocks >= 8) {
+  // Opt-in (TAPIR_B200_SPLITK=1).  Measured on the streaming step: a GEMM launch has ~12 us of fixed
+  // cost (prologue, pipeline fill, epilogue), so splitting K=2048 saves less than the reduce pass
+  // costs, and it makes results depend on the row count (exact chunk / streaming invariance lost).
+  static int splitk_on = -1;
+  if (splitk_on < 0) { const char* e = getenv("TAPIR_B200_SPLITK"); splitk_on = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
+  if (splitk_on && g.splitk_ws != nullptr && g.stats == nullptr && tiles * 2 <= sms && p.num_k_blocks >= 64) {
     int S = sms / tiles;
     if (S > 8) S = 8;
     if (S > p.num_k_blocks / 4) S = p.num_k_blocks / 4;
