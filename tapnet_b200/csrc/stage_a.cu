@@ -68,7 +68,6 @@ struct HeadSmem {
   float cv[(kG + 2) * (kG + 2)];     // zero-padded cost map
   float occ[16 * kOccPlane];         // ReLU(hid1) with halo, channel-major
   float w3[16 * 9 * 32];             // hid3 weights as [ci][tap][co]
-  float heat[kG * kG];
   float w1[16 * 9], b1[16], w2[16 * 9], b3[32];
   float w4[16 * 32], b4[16], w5[2 * 16], b5[2];
   float red_f[8 * 4];

@@ -88,3 +88,22 @@ def test_chunking_and_oracle_agreement_larger():
   e_e = (out['expected_dist'].cpu() - ref['expected_dist']).abs().max().item()
   U.record('e2e_oracle_T12_N96', tracks_err=e_t, occ_err=e_o, expd_err=e_e)
   assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_e < LOGIT_TOL
+
+
+def test_precision_modes():
+  """precision='bf16x6' (three bf16 terms, six MMAs) is fp32-equivalent; 'bf16' runs but is
+  outside the parity budget by design."""
+  g = load_golden('c1_bootstapir_256x8_n16')
+  meta = g['meta']
+  video, q = _inputs(meta)
+  m6, _, _ = get_model(precision='bf16x6')
+  out = m6(video.cuda(), q.cuda())
+  e_t = np.abs(out['tracks'][0].cpu().numpy() - g['tracks']).max()
+  e_o = np.abs(out['occlusion'][0].cpu().numpy() - g['occlusion']).max()
+  e_e = np.abs(out['expected_dist'][0].cpu().numpy() - g['expected_dist']).max()
+  m1, _, _ = get_model(precision='bf16')
+  out1 = m1(video.cuda(), q.cuda())
+  e1 = np.abs(out1['occlusion'][0].cpu().numpy() - g['occlusion']).max()
+  U.record('e2e_precision_modes', x6_tracks=e_t, x6_occ=e_o, x6_expd=e_e, x1_occ=e1)
+  assert e_t < 5e-4 and e_o < 3e-5 and e_e < 3e-5
+  assert torch.isfinite(out1['tracks']).all()
