@@ -461,6 +461,236 @@ gemm_tc_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------ 2-SM kernel
+// cta_group::2: a cluster of two CTAs (one TPC) computes a 256 x BN tile.  Each CTA loads its own
+// 128 rows of A and HALF of the B tile (BN/2 rows); the pair's tensor cores read both halves, so
+// the L2 -> SM operand requests per FLOP drop by 25 % (BN = 128) / 50 % (BN = 256) and a stage is
+// 48-64 KB.  One thread of the leader CTA (rank 0) issues the MMAs; TMA completions of both CTAs
+// land on the leader's full barrier; tcgen05.commit multicasts slot-free / accumulator-ready to
+// both CTAs; every CTA runs its own epilogue on its 128 TMEM lanes and reports back to the
+// leader's tmem_empty barrier.
+template <int BN, int P>
+struct Tc2Cfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBhBytes = (BN / 2) * kBlockK * 2;
+  static constexpr int kStageBytes = P * (kABytes + kBhBytes);
+  static constexpr int kEpiWarps = 16;
+  static constexpr int kChunks = BN / 32 / 4;
+  static constexpr int kBiasBytes = kEpiWarps * kChunks * 32 * 4;
+  static constexpr int kAvail = kSmemLimit - 1024 - kBarrierBytes - kBiasBytes;
+  static constexpr int kStagesRaw = kAvail / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarrierBytes + kBiasBytes;
+  static constexpr int kTmemCols = kNumAccStages * BN;  // 256 or 512
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static_assert(kStages >= 2, "tile does not fit in shared memory");
+  static_assert(BN == 128 || BN == 256, "pair tile width");
+};
+
+template <int BN, int P>
+__global__ void __launch_bounds__(Tc2Cfg<BN, P>::kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = Tc2Cfg<BN, P>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + kNumAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kNumAccStages);
+  float* bias_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + kBarrierBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  constexpr int kProducerWarp = Cfg::kEpiWarps;
+  constexpr int kMmaWarp = Cfg::kEpiWarps + 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);   // leader's producer (expect_tx for both CTAs' bytes)
+      ptx::mbar_init(&empty_bar[s], 1);  // pair commit, multicast
+    }
+    for (int a = 0; a < kNumAccStages; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);                    // pair commit, multicast
+      ptx::mbar_init(&tmem_empty_bar[a], 2 * Cfg::kEpiWarps);  // epilogue warps of BOTH CTAs
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&p.tmA);
+    ptx::prefetch_tensormap(&p.tmBh);
+  }
+  if (warp == kMmaWarp) {  // both CTAs, same warp id: collective allocation for the pair
+    ptx::tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkb = p.num_k_blocks;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_work = ((p.num_m_tiles + 1) / 2) * n_tiles;
+  const int work_first = (int)(blockIdx.x >> 1), work_stride = (int)(gridDim.x >> 1);
+  auto decode = [&](int w, int& m_tile, int& n0) {
+    const int mm = w / n_tiles;
+    m_tile = 2 * mm + rank;
+    n0 = (w - mm * n_tiles) * BN;
+  };
+
+  if (warp == kProducerWarp && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (each CTA)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = work_first; w < num_work; w += work_stride) {
+      int m_tile, n0;
+      decode(w, m_tile, n0);
+      int frame = 0, y0 = 0, x0 = 0;
+      if (p.mode == kGemmConv3x3) {
+        const int per_frame = p.tiles_x * p.tiles_y;
+        frame = m_tile / per_frame;
+        const int r = m_tile % per_frame;
+        y0 = (r / p.tiles_x) * p.tileH;
+        x0 = (r % p.tiles_x) * p.tileW;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 201);
+        if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + P * Cfg::kABytes;
+        if (p.mode == kGemmConv3x3) {
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          const int ky = tap / 3, kx = tap - ky * 3;
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl)
+            ptx::tma_load_5d_2sm(sa + pl * Cfg::kABytes, &p.tmA, &full_bar[stage], cb * kBlockK,
+                                 x0 + kx - 1, y0 + ky - 1, frame, pl);
+        } else {
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl)
+            ptx::tma_load_3d_2sm(sa + pl * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * kBlockK,
+                                 m_tile * kBlockM, pl);
+        }
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl)
+          ptx::tma_load_3d_2sm(sb + pl * Cfg::kBhBytes, &p.tmBh, &full_bar[stage], kb * kBlockK,
+                               n0 + rank * (BN / 2), pl);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == kMmaWarp && lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader only)
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * kBlockM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int w = work_first; w < num_work; w += work_stride, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, p.err, 202);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase, p.err, 203);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + P * Cfg::kABytes;
+        uint32_t accumulate = (kb > 0) ? 1u : 0u;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+#pragma unroll
+          for (int j = 0; j < P - i; ++j) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(sa + i * Cfg::kABytes);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + j * Cfg::kBhBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              ptx::umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+              accumulate = 1u;
+            }
+          }
+        }
+        ptx::umma_commit_2sm(&empty_bar[stage]);  // both producers may refill the slot
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+      ptx::umma_commit_2sm(&tmem_full_bar[acc]);  // both epilogues may read their TMEM half
+    }
+  } else if (warp < Cfg::kEpiWarps) {
+    // ------------------------------------------------------------------ epilogue (each CTA)
+    constexpr int kChunks = Cfg::kChunks;
+    const int q = warp & 3;
+    const int cbase = (warp >> 2) * kChunks;
+    float* bias_w = bias_smem + warp * (kChunks * 32);
+    int it = 0;
+    for (int w = work_first; w < num_work; w += work_stride, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int m_tile, n0;
+      decode(w, m_tile, n0);
+      const bool tile_valid = m_tile < p.num_m_tiles;
+      const int r = q * 32 + lane;
+      long long row;
+      bool row_ok;
+      int frame = 0;
+      if (p.mode == kGemmConv3x3) {
+        const int per_frame = p.tiles_x * p.tiles_y;
+        frame = m_tile / per_frame;
+        const int rr = m_tile % per_frame;
+        const int y = (rr / p.tiles_x) * p.tileH + r / p.tileW;
+        const int x = (rr % p.tiles_x) * p.tileW + r % p.tileW;
+        row_ok = (y < p.H) && (x < p.W) && tile_valid;
+        row = ((long long)frame * p.H + y) * p.W + x;
+      } else {
+        row = (long long)m_tile * kBlockM + r;
+        row_ok = row < p.M;
+        if (p.stats != nullptr) frame = (int)(((long long)m_tile * kBlockM) / p.rows_per_frame);
+      }
+      const int colbase = n0 + cbase * 32;
+      if (p.bias != nullptr) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kChunks; ++j) {
+          const int c = colbase + j * 32 + lane;
+          bias_w[j * 32 + lane] = (c < p.N) ? __ldg(p.bias + c) : 0.f;
+        }
+        __syncwarp();
+      }
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 204);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cbase * 32;
+      if (tile_valid && p.debug_mode != 1) {
+#pragma unroll 1
+        for (int i = 0; i < kChunks; ++i) {
+          const int col0 = colbase + i * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + i * 32, v);
+          ptx::tmem_ld_wait();
+          if (row_ok || p.stats != nullptr)
+            store_row_chunk(p, row, col0, v, bias_w + i * 32, row_ok, frame, lane, 0);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        else ptx::mbar_arrive_leader(&tmem_empty_bar[acc]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // no CTA may exit while the pair's MMAs / commits can still touch it
+  if (warp == kMmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+
 // Second pass of a split-K GEMM: sums the k-slice partials in a fixed order (deterministic) and
 // applies the epilogue (bias, GELU, residual, fp32 / bf16-plane outputs).
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int S,
@@ -614,6 +844,51 @@ int launch(const TcParams& p, const GemmArgs& g, cudaStream_t stream) {
   return kOk;
 }
 
+int use_2sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TAPIR_B200_GEMM_2SM");
+    v = e != nullptr ? atoi(e) : 0;  // 0 = off, 1 = auto width, 128 / 256 = forced pair-tile width
+  }
+  return v;
+}
+
+template <int BN, int P>
+int launch2(const TcParams& p, const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = Tc2Cfg<BN, P>;
+  static bool configured = false;
+  if (!configured) {
+    TAPIR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::kSmemBytes));
+    configured = true;
+  }
+  const double kl = g.k_logical > 0 ? g.k_logical : g.K;
+  const double out_b = (g.out_f32 ? 4.0 : 0.0) + (g.out_planes ? 2.0 * g.out_P : 0.0) + (g.residual ? 4.0 : 0.0);
+  const double a_elems = (g.mode == kGemmConv3x3) ? (double)g.M * g.C : (double)g.M * g.K;
+  ProfileScope ps(g.tag ? g.tag : "gemm", stream, 2.0 * g.M * g.N * kl,
+                  2.0 * P * (a_elems + (double)g.N * g.K) + out_b * g.M * g.N);
+  const int sms = num_sms();
+  const int pairs = ((p.num_m_tiles + 1) / 2) * ceil_div(g.N, BN);
+  const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TAPIR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BN, P>, p));
+  count_launch();
+  TAPIR_LAUNCH_CHECK("gemm_tc2_kernel");
+  return kOk;
+}
+
 int pick_block_n(int m_tiles, int N, int P) {
   const char* force = getenv("TAPIR_B200_BLOCK_N");
   if (force != nullptr) {
@@ -723,6 +998,31 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     TAPIR_RETURN_IF(encode_bf16_map(&p.tmB, g.b, 3, dims, str, box, "B"));
     cuuint32_t boxh[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(bn / 2), 1};
     TAPIR_RETURN_IF(encode_bf16_map(&p.tmBh, g.b, 3, dims, str, boxh, "B/half"));
+  }
+
+  // 2-SM path (cta_group::2): pair tiles of 256 x {128, 256}
+  if (use_2sm() != 0 && P <= 2 && g.N >= 128 && p.num_m_tiles >= 2 && (num_sms() % 2 == 0)) {
+    int bn2 = use_2sm();
+    if (bn2 != 128 && bn2 != 256) {
+      // auto: the wider tile halves the operand requests but doubles the wave quantum
+      const int half = num_sms() / 2;
+      const int pr = (p.num_m_tiles + 1) / 2;
+      const long long c128 = (long long)ceil_div(pr * ceil_div(g.N, 128), half) * 128;
+      const long long c256 = (long long)ceil_div(pr * ceil_div(g.N, 256), half) * 256;
+      bn2 = (g.N >= 256 && c256 * 9 <= c128 * 10) ? 256 : 128;
+    }
+    if (bn2 == 256 && g.N < 256) bn2 = 128;
+    const long long plane = g.b_plane_stride > 0 ? g.b_plane_stride : (long long)g.N * g.ldb;
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.N, (cuuint64_t)P};
+    cuuint64_t str[2] = {(cuuint64_t)g.ldb * 2, (cuuint64_t)plane * 2};
+    cuuint32_t boxh[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(bn2 / 2), 1};
+    TAPIR_RETURN_IF(encode_bf16_map(&p.tmBh, g.b, 3, dims, str, boxh, "B/2sm"));
+    p.split_k = 1;
+    p.split_stride = 0;
+    if (bn2 == 128 && P == 1) return launch2<128, 1>(p, g, stream);
+    if (bn2 == 128 && P == 2) return launch2<128, 2>(p, g, stream);
+    if (bn2 == 256 && P == 1) return launch2<256, 1>(p, g, stream);
+    if (bn2 == 256 && P == 2) return launch2<256, 2>(p, g, stream);
   }
 
   // split-K for problems that cannot fill the GPU (streaming: T = 1): deterministic two-pass
