@@ -848,7 +848,7 @@ int use_2sm() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TAPIR_B200_GEMM_2SM");
-    v = e != nullptr ? atoi(e) : 0;  // 0 = off, 1 = auto width, 128 / 256 = forced pair-tile width
+    v = e != nullptr ? atoi(e) : 1;  // 0 = off, 1 = auto width (default), 128 / 256 = forced width
   }
   return v;
 }
