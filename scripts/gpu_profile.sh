@@ -14,10 +14,10 @@ cap() {  # name, kernel regex, skip, count
 }
 # gemm launches per step: 20 resnet + 10 extra_conv + 1 cost volume + 4*(1+24+1) = 135
 cap mixer_dw mixer_dw_kernel 48 2
-cap gemm_extra gemm_tc_kernel $((135 + 20)) 2
-cap gemm_mixer gemm_tc_kernel $((135 + 32)) 2
+cap gemm_extra gemm_tc $((135 + 20)) 2
+cap gemm_mixer gemm_tc $((135 + 32)) 2
 cap local_corr local_corr_kernel 4 1
 cap head cost_volume_head 1 1
 cap instnorm_apply instnorm_relu_split_kernel 16 1
-cap cost_volume_gemm gemm_tc_kernel $((135 + 30)) 1
+cap cost_volume_gemm gemm_tc $((135 + 30)) 1
 ls -la gpurun_out/*.ncu-rep
