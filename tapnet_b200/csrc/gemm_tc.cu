@@ -1001,7 +1001,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   }
 
   // 2-SM path (cta_group::2): pair tiles of 256 x {128, 256}
-  if (use_2sm() != 0 && P <= 2 && g.N >= 128 && p.num_m_tiles >= 2 && (num_sms() % 2 == 0)) {
+  if (use_2sm() != 0 && g.N >= 128 && p.num_m_tiles >= 2 && (num_sms() % 2 == 0)) {
     int bn2 = use_2sm();
     if (bn2 != 128 && bn2 != 256) {
       // auto: the wider tile halves the operand requests but doubles the wave quantum
@@ -1023,6 +1023,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     if (bn2 == 128 && P == 2) return launch2<128, 2>(p, g, stream);
     if (bn2 == 256 && P == 1) return launch2<256, 1>(p, g, stream);
     if (bn2 == 256 && P == 2) return launch2<256, 2>(p, g, stream);
+    if (bn2 == 128 && P == 3) return launch2<128, 3>(p, g, stream);
+    if (bn2 == 256 && P == 3) return launch2<256, 3>(p, g, stream);
   }
 
   // split-K for problems that cannot fill the GPU (streaming: T = 1): deterministic two-pass
