@@ -215,6 +215,45 @@ int tapir_backbone_forward(const tapir_backbone_weights* w, const float* video, 
                            int32_t H, int32_t W, float* lowres, float* hires, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* Same, reading raw uint8 [0,255] frames: preprocess_frames (pytorch_live_demo.py:30-41,
+ * x / 255 * 2 - 1) is applied inside the stem conv's loads, the float video never exists. */
+int tapir_backbone_forward_u8(const tapir_backbone_weights* w, const uint8_t* video,
+                              int32_t frames, int32_t H, int32_t W, float* lowres, float* hires,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- frame ingest (the step before the path) ------------------------ */
+/* uint8 frames [frames][H][W][3] -> crop window (get_frame's centre square crop,
+ * pytorch_live_demo.py:88-95, or any window) -> preprocess_frames (:30-41) -> utils.bilinear
+ * (utils.py:26-42) to [frames][oH][oW][3] float in [-1,1]; one pass. */
+int tapir_ingest_frames(const uint8_t* src, int32_t frames, int32_t H, int32_t W, int32_t crop_y,
+                        int32_t crop_x, int32_t crop_h, int32_t crop_w, float* dst, int32_t oH,
+                        int32_t oW, void* stream);
+
+/* ---- output post-processing (the step after the path) ---------------- */
+/* pytorch_live_demo.py:57-59 / utils/model_utils.py:376-389:
+ * visible[i] = (1 - sigmoid(occ[i])) * (1 - sigmoid(expd[i])) > 0.5 */
+int tapir_postprocess_occlusions(const float* occ, const float* expd, int64_t n, uint8_t* visible,
+                                 void* stream);
+
+/* tapvid/evaluation_datasets.py:48-192 compute_tapvid_metrics, as exact integer counters per
+ * track; the host forms the ratios from their sums.  counts [B][N][TAPIR_TAPVID_COUNTERS]:
+ * [0] evaluated frames, [1] occlusion prediction correct, [2] ground-truth visible,
+ * [3+i] within 2^i px and visible, [8+i] true positives, [13+i] false positives (i = 0..4). */
+#define TAPIR_TAPVID_COUNTERS 18
+typedef struct {
+  const float* query_points;    /* [B][N][3]  (t, y, x) */
+  const uint8_t* gt_occluded;   /* [B][N][T]  bool */
+  const float* gt_tracks;       /* [B][N][T][2] (x, y) */
+  const uint8_t* pred_occluded; /* [B][N][T] bool, or NULL to threshold the two logit arrays */
+  const float* pred_occ_logits; /* [B][N][T] (used when pred_occluded is NULL) */
+  const float* pred_expd_logits;
+  const float* pred_tracks;     /* [B][N][T][2] */
+  int32_t B, N, T;
+  int32_t query_mode;           /* 0 = 'first', 1 = 'strided' */
+  int32_t* counts;
+} tapir_tapvid_args;
+int tapir_tapvid_counts(const tapir_tapvid_args* args, void* stream);
+
 /* ---- a4: tapir_model.py:217-291 + utils.py:45-73 (trilinear, border clamp) ---------- */
 /* query_tyx [N][3] in video coordinates (vT,vH,vW) -> out [N][C] */
 int tapir_sample_query_features(const float* grid, int32_t T, int32_t gh, int32_t gw, int32_t C,

@@ -26,6 +26,8 @@ for t in $TIERS; do
     e2e_simt)    run e2e_simt "TAPIR_B200_GEMM=simt" tests/test_end_to_end_gpu.py ;;
     e2e_tc)      run e2e_tc "X=1" tests/test_end_to_end_gpu.py ;;
     props)       run props "X=1" tests/test_properties_gpu.py ;;
+    io)          run io "X=1" tests/test_io_gpu.py ;;
+    bulk)        run bulk "X=1" tests/test_bulk_gpu.py ;;
     all)         run all "X=1" tests ;;
   esac
 done

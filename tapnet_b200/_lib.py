@@ -90,6 +90,16 @@ class UpdateArgs(Structure):
               ('tracks_out', c_void_p)]
 
 
+class TapvidArgs(Structure):
+  _fields_ = [('query_points', c_void_p), ('gt_occluded', c_void_p), ('gt_tracks', c_void_p),
+              ('pred_occluded', c_void_p), ('pred_occ_logits', c_void_p),
+              ('pred_expd_logits', c_void_p), ('pred_tracks', c_void_p),
+              ('B', c_int32), ('N', c_int32), ('T', c_int32), ('query_mode', c_int32),
+              ('counts', c_void_p)]
+
+
+TAPVID_COUNTERS = 18
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against
 # include/tapir_b200.h
 SIGNATURES = {
@@ -110,6 +120,14 @@ SIGNATURES = {
     'tapir_backbone_forward': (ctypes.c_int, [POINTER(BackboneWeights), c_void_p, c_int32, c_int32,
                                               c_int32, c_void_p, c_void_p, c_void_p, c_size_t,
                                               c_void_p]),
+    'tapir_backbone_forward_u8': (ctypes.c_int, [POINTER(BackboneWeights), c_void_p, c_int32,
+                                                 c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                                 c_size_t, c_void_p]),
+    'tapir_ingest_frames': (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                           c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    'tapir_postprocess_occlusions': (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p,
+                                                    c_void_p]),
+    'tapir_tapvid_counts': (ctypes.c_int, [POINTER(TapvidArgs), c_void_p]),
     'tapir_sample_query_features': (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32,
                                                    c_void_p, c_int32, c_int32, c_int32, c_int32,
                                                    c_void_p, c_void_p]),

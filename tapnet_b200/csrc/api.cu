@@ -79,7 +79,28 @@ size_t tapir_backbone_workspace_bytes(int32_t frames, int32_t H, int32_t W, int3
 int tapir_backbone_forward(const tapir_backbone_weights* w, const float* video, int32_t frames,
                            int32_t H, int32_t W, float* lowres, float* hires, void* workspace,
                            size_t workspace_bytes, void* stream) {
-  return backbone_forward(w, video, frames, H, W, lowres, hires, workspace, workspace_bytes, S(stream));
+  return backbone_forward(w, video, 0, frames, H, W, lowres, hires, workspace, workspace_bytes, S(stream));
+}
+
+int tapir_backbone_forward_u8(const tapir_backbone_weights* w, const uint8_t* video,
+                              int32_t frames, int32_t H, int32_t W, float* lowres, float* hires,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  return backbone_forward(w, video, 1, frames, H, W, lowres, hires, workspace, workspace_bytes, S(stream));
+}
+
+int tapir_ingest_frames(const uint8_t* src, int32_t frames, int32_t H, int32_t W, int32_t crop_y,
+                        int32_t crop_x, int32_t crop_h, int32_t crop_w, float* dst, int32_t oH,
+                        int32_t oW, void* stream) {
+  return ingest_frames(src, frames, H, W, crop_y, crop_x, crop_h, crop_w, dst, oH, oW, S(stream));
+}
+
+int tapir_postprocess_occlusions(const float* occ, const float* expd, int64_t n, uint8_t* visible,
+                                 void* stream) {
+  return postprocess_occlusions(occ, expd, n, visible, S(stream));
+}
+
+int tapir_tapvid_counts(const tapir_tapvid_args* args, void* stream) {
+  return tapvid_counts(args, S(stream));
 }
 
 int tapir_sample_query_features(const float* grid, int32_t T, int32_t gh, int32_t gw, int32_t C,

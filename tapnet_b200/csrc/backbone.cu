@@ -33,7 +33,16 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long long ld_
 constexpr int kStemTile = 16;
 constexpr int kStemPatch = 2 * kStemTile + 5;  // 37 input pixels per side
 
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ video,
+// In = float: video already in [-1,1].  In = uint8_t: raw [0,255] frames, normalised on load
+// exactly like preprocess_frames (pytorch_live_demo.py:30-41: x / 255 * 2 - 1, fp32, each
+// operation rounded) so that the float tensor never exists in HBM.
+__device__ __forceinline__ float stem_load(const float* p) { return *p; }
+__device__ __forceinline__ float stem_load(const uint8_t* p) {
+  return __fsub_rn(__fmul_rn(__fdiv_rn((float)*p, 255.f), 2.f), 1.f);
+}
+
+template <typename In>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const In* __restrict__ video,
                                                         const float* __restrict__ w, int H, int W,
                                                         float* __restrict__ out) {
   extern __shared__ float stem_smem[];
@@ -48,7 +57,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     const int c = i % 3, px = (i / 3) % kStemPatch, py = i / (3 * kStemPatch);
     const int y = iy0 + py, x = ix0 + px;
     float v = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) v = video[(((long long)f * H + y) * W + x) * 3 + c];
+    if (y >= 0 && y < H && x >= 0 && x < W) v = stem_load(video + (((long long)f * H + y) * W + x) * 3 + c);
     patch[i] = v;
   }
   __syncthreads();
@@ -350,19 +359,24 @@ int split_planes(const float* src, long long ld_src, __nv_bfloat16* dst, long lo
   return kOk;
 }
 
-int stem_conv(const float* video, const float* w_packed, int frames, int H, int W, float* out,
-              cudaStream_t s) {
+int stem_conv(const void* video, int video_u8, const float* w_packed, int frames, int H, int W,
+              float* out, cudaStream_t s) {
   TAPIR_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "stem_conv: H, W must be even");
   const int smem = (147 * 64 + kStemPatch * kStemPatch * 3) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
-    TAPIR_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TAPIR_CUDA(cudaFuncSetAttribute(stem_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TAPIR_CUDA(cudaFuncSetAttribute(stem_conv_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   ProfileScope ps("backbone.stem_conv", s, 2.0 * frames * (H / 2) * (W / 2) * 64 * 147,
-                  (double)frames * H * W * 3 * 4 + (double)frames * (H / 2) * (W / 2) * 64 * 4);
+                  (double)frames * H * W * 3 * (video_u8 ? 1 : 4) +
+                      (double)frames * (H / 2) * (W / 2) * 64 * 4);
   dim3 grid(ceil_div(W / 2, kStemTile), ceil_div(H / 2, kStemTile), frames);
-  stem_conv_kernel<<<grid, 256, smem, s>>>(video, w_packed, H, W, out);
+  if (video_u8)
+    stem_conv_kernel<uint8_t><<<grid, 256, smem, s>>>(static_cast<const uint8_t*>(video), w_packed, H, W, out);
+  else
+    stem_conv_kernel<float><<<grid, 256, smem, s>>>(static_cast<const float*>(video), w_packed, H, W, out);
   count_launch();
   TAPIR_LAUNCH_CHECK("stem_conv_kernel");
   return kOk;
@@ -519,8 +533,9 @@ size_t backbone_workspace_bytes(int frames, int H, int W, int extra_convs, int p
   return plan_backbone(a, frames, H, W, extra_convs, planes, &bp) + 256;
 }
 
-int backbone_forward(const tapir_backbone_weights* w, const float* video, int frames, int H, int W,
-                     float* lowres, float* hires, void* ws, size_t ws_bytes, cudaStream_t s) {
+int backbone_forward(const tapir_backbone_weights* w, const void* video, int video_u8, int frames,
+                     int H, int W, float* lowres, float* hires, void* ws, size_t ws_bytes,
+                     cudaStream_t s) {
   TAPIR_CHECK_ARG(w != nullptr && video != nullptr && lowres != nullptr && hires != nullptr,
                   "backbone_forward: null pointer");
   TAPIR_CHECK_ARG(frames > 0 && H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16,
@@ -537,7 +552,7 @@ int backbone_forward(const tapir_backbone_weights* w, const float* video, int fr
 
   int h = H / 2, wd = W / 2;
   float* x = bp.buf[0];
-  TAPIR_RETURN_IF(stem_conv(video, w->stem_w, frames, H, W, x, s));
+  TAPIR_RETURN_IF(stem_conv(video, video_u8, w->stem_w, frames, H, W, x, s));
   int xi = 0;  // index of the buffer holding x
   // InstanceNorm statistics are accumulated by the epilogue of the GEMM that produces the
   // tensor (fp64 atomics into bp.sums); only the stem output needs the stand-alone pass.

@@ -28,8 +28,8 @@ struct Arena {
 int split_planes(const float* src, long long ld_src, __nv_bfloat16* dst, long long ld_dst,
                  long long plane_stride, long long rows, int cols, int cols_padded, int planes,
                  cudaStream_t s);
-int stem_conv(const float* video, const float* w_packed, int frames, int H, int W, float* out,
-              cudaStream_t s);
+int stem_conv(const void* video, int video_u8, const float* w_packed, int frames, int H, int W,
+              float* out, cudaStream_t s);
 int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, const float* w,
                    const float* b, float* mr, cudaStream_t s);
 int instnorm_zero(int frames, int C, double* sums, cudaStream_t s);
@@ -46,8 +46,16 @@ int l2_normalize(const float* x, long long rows, int C, float* out, cudaStream_t
 int bilinear_resize(const float* src, int frames, int H, int W, int C, float* dst, int oH, int oW,
                     cudaStream_t s);
 size_t backbone_workspace_bytes(int frames, int H, int W, int extra_convs, int planes);
-int backbone_forward(const tapir_backbone_weights* w, const float* video, int frames, int H, int W,
-                     float* lowres, float* hires, void* ws, size_t ws_bytes, cudaStream_t s);
+int backbone_forward(const tapir_backbone_weights* w, const void* video, int video_u8, int frames,
+                     int H, int W, float* lowres, float* hires, void* ws, size_t ws_bytes,
+                     cudaStream_t s);
+
+// ---- callers either side of the path (frames_io.cu) ----------------
+int ingest_frames(const uint8_t* src, int frames, int H, int W, int crop_y, int crop_x, int crop_h,
+                  int crop_w, float* dst, int oH, int oW, cudaStream_t s);
+int postprocess_occlusions(const float* occ, const float* expd, long long n, uint8_t* visible,
+                           cudaStream_t s);
+int tapvid_counts(const tapir_tapvid_args* a, cudaStream_t s);
 
 // ---- stage A (stage_a.cu) ---------------------------------------------------------------
 int sample_query_features(const float* grid, int T, int gh, int gw, int C, const float* query_tyx,

@@ -340,7 +340,12 @@ class TAPIR(nn.Module):
     dev = self._device_check(video)
     lib = _lib.load()
     pk = self._pack()
-    video = video.to(torch.float32).contiguous()
+    # uint8 video = raw [0,255] frames (what the reference's callers hold before
+    # preprocess_frames, pytorch_live_demo.py:30-41): normalised inside the stem conv's loads
+    # (or inside the resize), so the 4x larger float video never exists.  Extension of the
+    # reference surface; float video behaves exactly as before.
+    video_u8 = video.dtype == torch.uint8
+    video = video.contiguous() if video_u8 else video.to(torch.float32).contiguous()
     n, f, vh, vw, _ = video.shape
     feature_grid, hires_feats, resize_im_shape = [], [], []
     curr_resolution = (-1, -1)
@@ -361,8 +366,14 @@ class TAPIR(nn.Module):
             frames_src = video  # align_corners=False resize to the same size is the identity
           else:
             frames_src = torch.empty(n, f, h, w, 3, dtype=torch.float32, device=dev)
-            _lib.check(lib.tapir_bilinear_resize(_ptr(video), n * f, vh, vw, 3, _ptr(frames_src),
-                                                 h, w, stream), 'tapir_bilinear_resize')
+            if video_u8:
+              _lib.check(lib.tapir_ingest_frames(_ptr(video), n * f, vh, vw, 0, 0, vh, vw,
+                                                 _ptr(frames_src), h, w, stream),
+                         'tapir_ingest_frames')
+            else:
+              _lib.check(lib.tapir_bilinear_resize(_ptr(video), n * f, vh, vw, 3,
+                                                   _ptr(frames_src), h, w, stream),
+                         'tapir_bilinear_resize')
         if h % 8 != 0 or w % 8 != 0:
           raise ValueError('Image resolution must be a multiple of 8.')
         curr_resolution = resolution
@@ -382,9 +393,11 @@ class TAPIR(nn.Module):
         ws = self._workspace('backbone', nbytes, dev)
         for s0 in range(0, nf, chunk):
           c = min(chunk, nf - s0)
-          _lib.check(lib.tapir_backbone_forward(
-              ctypes.byref(pk['backbone']), _ptr(flat_src[s0:]), c, h, w, _ptr(flat_lo[s0:]),
-              _ptr(flat_hi[s0:]), _ptr(ws), ws.numel(), stream), 'tapir_backbone_forward')
+          fwd = (lib.tapir_backbone_forward_u8 if flat_src.dtype == torch.uint8
+                 else lib.tapir_backbone_forward)
+          _lib.check(fwd(ctypes.byref(pk['backbone']), _ptr(flat_src[s0:]), c, h, w,
+                         _ptr(flat_lo[s0:]), _ptr(flat_hi[s0:]), _ptr(ws), ws.numel(), stream),
+                     'tapir_backbone_forward')
       feature_grid.append(latent)
       hires_feats.append(hires)
       resize_im_shape.append(torch.Size(shape_hw))
