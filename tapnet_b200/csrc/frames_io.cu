@@ -63,10 +63,20 @@ __global__ void __launch_bounds__(256) ingest_frames_kernel(const uint8_t* __res
   for (long long i0 = blockIdx.x * 256LL; i0 < total; i0 += (long long)gridDim.x * 256) {
     const long long i = i0 + threadIdx.x;
     if (i < total) {
-      const int ox = (int)(i % oW);
-      long long r = i / oW;
-      const int oy = (int)(r % oH);
-      const long long f = r / oH;
+      int ox, oy;
+      long long f;
+      if (total <= 0x7fffffffLL) {  // 32-bit divisions (the 64-bit ones cost more than the loads)
+        const unsigned u = (unsigned)i, r = u / (unsigned)oW;
+        ox = (int)(u - r * (unsigned)oW);
+        const unsigned q = r / (unsigned)oH;
+        oy = (int)(r - q * (unsigned)oH);
+        f = q;
+      } else {
+        ox = (int)(i % oW);
+        const long long r = i / oW;
+        oy = (int)(r % oH);
+        f = r / oH;
+      }
       const uint8_t* b = src + (f * H + cy) * (long long)W * 3 + (long long)cx * 3;
       float* o = stage + threadIdx.x * 3;
       if (same) {
