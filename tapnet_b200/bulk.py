@@ -139,7 +139,8 @@ def track_many_points(separation_videos: Mapping, demo_episode_ids: Sequence, ch
 
   Args follow tapir_clustering.py:1023-1044; `checkpoint_path` may also be an already-built
   causal `TAPIR` module.  Extra: `frames_per_step` (frames advanced per launch sequence),
-  `group` (torch.distributed group to share the batches over), `device`.
+  `group` (torch.distributed group to share the batches over; None = the default group when
+  torch.distributed is initialised, False = this process alone), `device`.
 
   Returns the reference's dictionary, values as numpy arrays: 'separation_visibility'
   {id: [points, T_id] bool}, 'separation_tracks' {id: [points, T_id, 2]}, 'video_shape',
@@ -157,7 +158,10 @@ def track_many_points(separation_videos: Mapping, demo_episode_ids: Sequence, ch
   if dev.type != 'cuda':
     raise RuntimeError('track_many_points runs on CUDA only (no CPU fallback)')
   rank, world = 0, 1
-  if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+  if group is False:        # force single-process execution inside an initialised job
+    group = None
+  elif group is not None or (torch.distributed.is_available()
+                             and torch.distributed.is_initialized()):
     rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
 
   videos = [_as_u8_device(separation_videos[k], dev) for k in demo_episode_ids]
