@@ -28,6 +28,19 @@ import torch  # noqa: E402
 T_FRAMES, RES, Q_PER_GPU = 48, 256, 256
 METRIC = 'query-points x frames / sec (TAPIR inference, 256x256x48)'
 UNIT = 'point-frames/s'
+SCALING, CONFIG_NAME = 'weak', 'BASELINE.json configs[1]'
+
+
+def select_workload(name):
+  """c2 (default, the driver's contract): 256x256x48, 256 queries per GPU, weak scaling.
+  c4 (BASELINE.json configs[3], the north star's scaling target): 256x256x96, 4096 queries in
+  total shared by the ranks, strong scaling."""
+  global T_FRAMES, Q_PER_GPU, METRIC, SCALING, CONFIG_NAME
+  if name == 'c4':
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    T_FRAMES, Q_PER_GPU = 96, 4096 // world
+    METRIC = 'query-points x frames / sec (TAPIR inference, 256x256x96, 4096 queries)'
+    SCALING, CONFIG_NAME = 'strong', 'BASELINE.json configs[3]'
 
 
 def _peaks():
@@ -38,6 +51,10 @@ def _peaks():
     return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sustained=d['bf16_tflops_sustained'],
                 source='measured (MEASURED_PEAKS.json)')
   return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+# bf16 MMAs issued per fp32-equivalent product term under each precision policy
+_MMA_TERMS = {'bf16': 1, 'bf16x3': 3, 'bf16x6': 6}
 
 
 class ClockSampler:
@@ -267,6 +284,10 @@ def run_ours(args):
                       unit='TFLOP/s', frac=round(ach / peaks['tf_sustained'], 4), traffic=traffic,
                       peak_source=peaks['source'] + ', sustained (kernel timed inside a long step)',
                       launches=v['launches'] // 2, avg_launch_ms=round(v['ms'] / v['launches'], 4),
+                      mma_terms=_MMA_TERMS[args.precision],
+                      issued_mma_tflops=round(ach * _MMA_TERMS[args.precision], 1),
+                      issued_mma_frac_of_burst_peak=round(
+                          ach * _MMA_TERMS[args.precision] / peaks['tf_burst'], 4),
                       note='achieved counts ALGORITHMIC fp32-equivalent FLOPs (2*M*N*K); the kernel '
                            'issues 3 bf16 MMAs per product term (split-bf16, required by the 1e-4 '
                            'parity budget), so tensor-pipe work is 3x this figure')
@@ -279,10 +300,10 @@ def run_ours(args):
   line = dict(
       metric=METRIC, value=round(units / (ms_step * 1e-3), 1), unit=UNIT, n_gpus=world,
       steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=round(ms_step, 3),
-      higher_is_better=True, scaling='weak', vs_baseline=None,
+      higher_is_better=True, scaling=SCALING, vs_baseline=None,
       dtype='bf16x3' if args.precision == 'bf16x3' else args.precision, data='synthetic',
       config=dict(workload=f'TAPIR/BootsTAPIR inference {RES}x{RES}x{T_FRAMES}, {Q_PER_GPU} query '
-                           f'points per GPU ({N} total), BASELINE.json configs[1]',
+                           f'points per GPU ({N} total), {CONFIG_NAME}',
                   frames=T_FRAMES, resolution=RES, queries=N, refine_iterations=4,
                   parallelism=f'frame-shard backbone + all-gather + query-shard x{world}',
                   l2='256 MiB buffer written between timed steps (L2 flush)',
@@ -393,9 +414,9 @@ def run_reference(args):
   base['value'] = v
   line = dict(impl='reference', metric=METRIC, value=v, unit=UNIT, n_gpus=world, steps=args.steps,
               warmup=args.warmup, ms_per_step=round(N * T_FRAMES / v * 1e3, 1), higher_is_better=True,
-              scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+              scaling=SCALING, vs_baseline=None, dtype='f32', data='synthetic',
               config=dict(workload=f'TAPIR/BootsTAPIR inference {RES}x{RES}x{T_FRAMES}, {Q_PER_GPU} query '
-                                   f'points per GPU ({N} total), BASELINE.json configs[1]',
+                                   f'points per GPU ({N} total), {CONFIG_NAME}',
                           frames=T_FRAMES, resolution=RES, queries=N, refine_iterations=4),
               cpu_baseline=base,
               e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -410,7 +431,10 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--precision', default='bf16x3', choices=['bf16', 'bf16x3', 'bf16x6'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+  ap.add_argument('--workload', default='c2', choices=['c2', 'c4'],
+                  help='c2 = driver contract (default); c4 = 4096 queries x 96 frames, strong scaling')
   args = ap.parse_args()
+  select_workload(args.workload)
   if args.impl == 'reference':
     run_reference(args)
   else:
