@@ -20,4 +20,5 @@ cap local_corr local_corr_kernel 4 1
 cap head cost_volume_head 1 1
 cap instnorm_apply instnorm_relu_split_kernel 16 1
 cap cost_volume_gemm gemm_tc $((135 + 30)) 1
+cap stem stem_conv_kernel 1 1
 ls -la gpurun_out/*.ncu-rep

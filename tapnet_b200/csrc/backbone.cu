@@ -29,9 +29,13 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long long ld_
 
 // ------------------------------------------------------------------------ stem conv
 // nets.py:395-402,420: F.pad(x,(2,4,2,4)) then 7x7 stride-2 conv, 3 -> 64, no bias.
-// CTA = 16x16 output pixels; each thread owns one pixel and all 64 output channels.
-constexpr int kStemTile = 16;
-constexpr int kStemPatch = 2 * kStemTile + 5;  // 37 input pixels per side
+// CTA = 16 x 32 output pixels; each thread owns two pixels of a row (16 apart) and all 64
+// output channels (one broadcast LDS.128 of weights feeds 8 FMAs; with one pixel per thread the
+// kernel was bound by the shared-memory pipe, not the FMA pipe).
+constexpr int kStemTileY = 16;
+constexpr int kStemTileX = 32;
+constexpr int kStemPatchY = 2 * kStemTileY + 5;  // 37 input rows
+constexpr int kStemPatchX = 2 * kStemTileX + 5;  // 69 input columns
 
 // In = float: video already in [-1,1].  In = uint8_t: raw [0,255] frames, normalised on load
 // exactly like preprocess_frames (pytorch_live_demo.py:30-41: x / 255 * 2 - 1, fp32, each
@@ -42,52 +46,63 @@ __device__ __forceinline__ float stem_load(const uint8_t* p) {
 }
 
 template <typename In>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const In* __restrict__ video,
-                                                        const float* __restrict__ w, int H, int W,
-                                                        float* __restrict__ out) {
+__global__ void __launch_bounds__(256, 1) stem_conv_kernel(const In* __restrict__ video,
+                                                           const float* __restrict__ w, int H, int W,
+                                                           float* __restrict__ out) {
   extern __shared__ float stem_smem[];
   float* ws = stem_smem;                    // [147][64]
-  float* patch = stem_smem + 147 * 64;      // [37][37][3]
+  float* patch = stem_smem + 147 * 64;      // [37][69][3]
   const int OH = H / 2, OW = W / 2;
   const int f = blockIdx.z;
-  const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
+  const int oy0 = blockIdx.y * kStemTileY, ox0 = blockIdx.x * kStemTileX;
   for (int i = threadIdx.x; i < 147 * 64; i += 256) ws[i] = w[i];
   const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
-  for (int i = threadIdx.x; i < kStemPatch * kStemPatch * 3; i += 256) {
-    const int c = i % 3, px = (i / 3) % kStemPatch, py = i / (3 * kStemPatch);
+  for (int i = threadIdx.x; i < kStemPatchY * kStemPatchX * 3; i += 256) {
+    const int c = i % 3, px = (i / 3) % kStemPatchX, py = i / (3 * kStemPatchX);
     const int y = iy0 + py, x = ix0 + px;
     float v = 0.f;
     if (y >= 0 && y < H && x >= 0 && x < W) v = stem_load(video + (((long long)f * H + y) * W + x) * 3 + c);
     patch[i] = v;
   }
   __syncthreads();
-  const int ty = threadIdx.x / kStemTile, tx = threadIdx.x % kStemTile;
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  float acc[64];
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;  // pixels (ty, tx) and (ty, tx + 16)
+  float acc0[64], acc1[64];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 64; ++i) acc0[i] = acc1[i] = 0.f;
   for (int ky = 0; ky < 7; ++ky) {
     for (int kx = 0; kx < 7; ++kx) {
-      const float* pp = patch + ((2 * ty + ky) * kStemPatch + (2 * tx + kx)) * 3;
+      const float* pp = patch + ((2 * ty + ky) * kStemPatchX + (2 * tx + kx)) * 3;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float v = pp[c];
+        const float v0 = pp[c], v1 = pp[c + 2 * 16 * 3];
         const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 7 + kx) * 3 + c) * 64);
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
           const float4 w4 = wr[o];
-          acc[4 * o + 0] = fmaf(v, w4.x, acc[4 * o + 0]);
-          acc[4 * o + 1] = fmaf(v, w4.y, acc[4 * o + 1]);
-          acc[4 * o + 2] = fmaf(v, w4.z, acc[4 * o + 2]);
-          acc[4 * o + 3] = fmaf(v, w4.w, acc[4 * o + 3]);
+          acc0[4 * o + 0] = fmaf(v0, w4.x, acc0[4 * o + 0]);
+          acc0[4 * o + 1] = fmaf(v0, w4.y, acc0[4 * o + 1]);
+          acc0[4 * o + 2] = fmaf(v0, w4.z, acc0[4 * o + 2]);
+          acc0[4 * o + 3] = fmaf(v0, w4.w, acc0[4 * o + 3]);
+          acc1[4 * o + 0] = fmaf(v1, w4.x, acc1[4 * o + 0]);
+          acc1[4 * o + 1] = fmaf(v1, w4.y, acc1[4 * o + 1]);
+          acc1[4 * o + 2] = fmaf(v1, w4.z, acc1[4 * o + 2]);
+          acc1[4 * o + 3] = fmaf(v1, w4.w, acc1[4 * o + 3]);
         }
       }
     }
   }
-  if (oy < OH && ox < OW) {
-    float4* o = reinterpret_cast<float4*>(out + (((long long)f * OH + oy) * OW + ox) * 64);
+  const int oy = oy0 + ty;
+  if (oy < OH) {
+    if (ox0 + tx < OW) {
+      float4* o = reinterpret_cast<float4*>(out + (((long long)f * OH + oy) * OW + ox0 + tx) * 64);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+      for (int i = 0; i < 16; ++i) o[i] = make_float4(acc0[4 * i], acc0[4 * i + 1], acc0[4 * i + 2], acc0[4 * i + 3]);
+    }
+    if (ox0 + tx + 16 < OW) {
+      float4* o = reinterpret_cast<float4*>(out + (((long long)f * OH + oy) * OW + ox0 + tx + 16) * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = make_float4(acc1[4 * i], acc1[4 * i + 1], acc1[4 * i + 2], acc1[4 * i + 3]);
+    }
   }
 }
 
@@ -362,7 +377,7 @@ int split_planes(const float* src, long long ld_src, __nv_bfloat16* dst, long lo
 int stem_conv(const void* video, int video_u8, const float* w_packed, int frames, int H, int W,
               float* out, cudaStream_t s) {
   TAPIR_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "stem_conv: H, W must be even");
-  const int smem = (147 * 64 + kStemPatch * kStemPatch * 3) * (int)sizeof(float);
+  const int smem = (147 * 64 + kStemPatchY * kStemPatchX * 3) * (int)sizeof(float);
   static bool configured = false;
   if (!configured) {
     TAPIR_CUDA(cudaFuncSetAttribute(stem_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -372,7 +387,7 @@ int stem_conv(const void* video, int video_u8, const float* w_packed, int frames
   ProfileScope ps("backbone.stem_conv", s, 2.0 * frames * (H / 2) * (W / 2) * 64 * 147,
                   (double)frames * H * W * 3 * (video_u8 ? 1 : 4) +
                       (double)frames * (H / 2) * (W / 2) * 64 * 4);
-  dim3 grid(ceil_div(W / 2, kStemTile), ceil_div(H / 2, kStemTile), frames);
+  dim3 grid(ceil_div(W / 2, kStemTileX), ceil_div(H / 2, kStemTileY), frames);
   if (video_u8)
     stem_conv_kernel<uint8_t><<<grid, 256, smem, s>>>(static_cast<const uint8_t*>(video), w_packed, H, W, out);
   else

@@ -98,8 +98,12 @@ __global__ void __launch_bounds__(96) local_corr_kernel(const CorrParams p) {
   __shared__ float corr[TAPIR_MAX_CORR_LEVELS * 49];
   const tapir_corr_args& a = p.a;
   const int T = a.num_frames;
-  const long long row = blockIdx.x;
-  const int n = (int)(row / T), t = (int)(row - (long long)n * T);
+  // CTAs are issued frame-major: the CTAs resident at any time read the grids of one or two
+  // frames (3.3 MB per frame at 256^2), which therefore stay in L2; the row order (n, t) of the
+  // inputs / outputs would cycle through every frame's grids (all of them exceed L2) per query.
+  const int t = (int)(blockIdx.x / (unsigned)a.num_points);
+  const int n = (int)(blockIdx.x - (unsigned)t * (unsigned)a.num_points);
+  const long long row = (long long)n * T + t;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float px = a.pos[row * 2 + 0], py = a.pos[row * 2 + 1];
   const float* fhi = a.feat_hi + n * a.feat_hi_stride_n + t * a.feat_hi_stride_t;
@@ -315,13 +319,19 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
     }
     float y0 = yq[0], y1 = yq[512];
     float ha[4], hb[4], hc[4];
+    // h1 of frame f = first + j.  CHECKED handles sequence ends (zero padding / causal context /
+    // context output); the unchecked form is the same arithmetic without the tests, so a frame
+    // gives the same bits whichever form computes it (chunk invariance stays exact).
+    auto h1_math = [&](float y2, float (&o)[4]) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        o[m] = gelu_tanh(fmaf(w1[m][2], y2, fmaf(w1[m][1], y1, fmaf(w1[m][0], y0, b1[m]))));
+    };
     auto h1 = [&](int j, float (&o)[4]) {
       const int f = first + j;
       const float y2 = yq[(j + 2) * 512];
       if (f >= 0 && f < T) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-          o[m] = gelu_tanh(fmaf(w1[m][2], y2, fmaf(w1[m][1], y1, fmaf(w1[m][0], y0, b1[m]))));
+        h1_math(y2, o);
         if (CAUSAL && p.ctx2_out != nullptr && f >= T - 2)  // last two frames of [ctx | h1] (nets.py:167)
           *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + (f - (T - 2))) * 2048 + 4 * c) =
               make_float4(o[0], o[1], o[2], o[3]);
@@ -334,22 +344,52 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
       y0 = y1;
       y1 = y2;
     };
-    h1(0, ha);
-    h1(1, hb);
-    const float* xq = xraw + q * TT * 512 + c;
-#pragma unroll 2
-    for (int i = 0; i < t1 - t0; ++i) {
-      h1(i + 2, hc);
-      float acc = xq[i * 512];
+    // second conv + group sum + skip for output frame i, from h1 of frames i-1, i, i+1 (a, b, c);
+    // rows <= i + 2 of this column are dead by then: z[t0 + i] is parked in row i
+    auto emit = [&](float* yrow, const float* xrow, float* zrow, const float (&a)[4],
+                    const float (&b)[4], const float (&cc)[4]) {
+      float acc = *xrow;
 #pragma unroll
       for (int m = 0; m < 4; ++m)
-        acc += fmaf(w2[m][2], hc[m], fmaf(w2[m][1], hb[m], fmaf(w2[m][0], ha[m], b2[m])));
-      // rows <= i + 2 of this column are dead by now: park z[t0 + i] in row i
-      yq[i * 512] = acc;
-      p.z[((long long)n * T + t0 + i) * 512 + c] = acc;
+        acc += fmaf(w2[m][2], cc[m], fmaf(w2[m][1], b[m], fmaf(w2[m][0], a[m], b2[m])));
+      *yrow = acc;
+      *zrow = acc;
+    };
+    h1(0, ha);
+    h1(1, hb);
+    const int nout = t1 - t0;
+    // output frames whose newest h1 frame (first + i + 2) needs no end-of-sequence handling
+    int i_lo = max(0, -(first + 2));
+    int i_hi = min(nout, ((CAUSAL && p.ctx2_out != nullptr) ? T - 2 : T) - (first + 2));
+    if (i_hi < i_lo) i_lo = i_hi = 0;
+    float* yp = yq;
+    const float* xp = xraw + q * TT * 512 + c;
+    float* zp = p.z + ((long long)n * T + t0) * 512 + c;
+    int i = 0;
+    auto checked_until = [&](int stop) {
+      for (; i < stop; ++i, yp += 512, xp += 512, zp += 512) {
+        h1(i + 2, hc);
+        emit(yp, xp, zp, ha, hb, hc);
 #pragma unroll
-      for (int m = 0; m < 4; ++m) { ha[m] = hb[m]; hb[m] = hc[m]; }
+        for (int m = 0; m < 4; ++m) { ha[m] = hb[m]; hb[m] = hc[m]; }
+      }
+    };
+    checked_until(i_lo);
+    // interior, three frames per trip: the roles of (ha, hb, hc) rotate back after three steps,
+    // so no register moves and no tests
+    for (; i + 3 <= i_hi; i += 3, yp += 1536, xp += 1536, zp += 1536) {
+      const float ya = yp[4 * 512], yb = yp[5 * 512], yc = yp[6 * 512];
+      h1_math(ya, hc);
+      y0 = y1; y1 = ya;
+      emit(yp, xp, zp, ha, hb, hc);
+      h1_math(yb, ha);
+      y0 = y1; y1 = yb;
+      emit(yp + 512, xp + 512, zp + 512, hb, hc, ha);
+      h1_math(yc, hb);
+      y0 = y1; y1 = yc;
+      emit(yp + 1024, xp + 1024, zp + 1024, hc, ha, hb);
     }
+    checked_until(nout);
   }
   __syncthreads();
 
