@@ -68,7 +68,10 @@ struct HeadSmem {
   float cv[(kG + 2) * (kG + 2)];     // zero-padded cost map
   float occ[16 * kOccPlane];         // ReLU(hid1) with halo, channel-major
   float w3[16 * 9 * 32];             // hid3 weights as [ci][tap][co]
-  float w1[16 * 9], b1[16], w2[16 * 9], b3[32];
+  // hid1 / hid2 weights, 9 taps padded to 12 per channel: three broadcast LDS.128 per channel
+  __align__(16) float w1[16 * 12];
+  __align__(16) float w2[16 * 12];
+  float b1[16], b3[32];
   float w4[16 * 32], b4[16], w5[2 * 16], b5[2];
   float red_f[8 * 4];
   int red_i[8];
@@ -137,7 +140,11 @@ __global__ void __launch_bounds__(256) cost_volume_head_kernel(
     const int co = i & 31, tap = (i >> 5) % 9, ci = i / (32 * 9);
     sm.w3[i] = w.hid3_w[(co * 16 + ci) * 9 + tap];
   }
-  if (tid < 144) { sm.w1[tid] = w.hid1_w[tid]; sm.w2[tid] = w.hid2_w[tid]; }
+  if (tid < 192) {
+    const int co = tid / 12, k = tid - co * 12;
+    sm.w1[tid] = (k < 9) ? w.hid1_w[co * 9 + k] : 0.f;
+    sm.w2[tid] = (k < 9) ? w.hid2_w[co * 9 + k] : 0.f;
+  }
   if (tid < 16) { sm.b1[tid] = w.hid1_b[tid]; sm.b4[tid] = w.hid4_b[tid]; }
   if (tid < 32) { sm.b3[tid] = w.hid3_b[tid]; sm.w5[tid] = w.occ_w[tid]; }
   if (tid < 2) sm.b5[tid] = w.occ_b[tid];
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(256) cost_volume_head_kernel(
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float wv = sm.w1[co * 9 + ky * 3 + kx];
+          const float wv = sm.w1[co * 12 + ky * 3 + kx];
 #pragma unroll
           for (int p = 0; p < 4; ++p) a[p] = fmaf(win[ky][kx + p], wv, a[p]);
         }
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(256) cost_volume_head_kernel(
         for (int c = 0; c < 6; ++c) row[c] = op[(y + ky) * kOccW + x0 + c];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float wv = sm.w2[ci * 9 + ky * 3 + kx];
+          const float wv = sm.w2[ci * 12 + ky * 3 + kx];
 #pragma unroll
           for (int p = 0; p < 4; ++p) a[p] = fmaf(row[kx + p], wv, a[p]);
         }
@@ -322,7 +329,10 @@ struct HeadTcSmem {
   float stap[9 * kTapW];
   uint32_t occ_hi[kPlaneWords], occ_lo[kPlaneWords];
   uint32_t w3_hi[9 * 32 * kPixW], w3_lo[9 * 32 * kPixW];  // [tap][co][ci pairs]
-  float w1[16 * 9], b1[16], w2[16 * 9], b3[32];
+  // hid1 / hid2 weights, 9 taps padded to 12 per channel: three broadcast LDS.128 per channel
+  __align__(16) float w1[16 * 12];
+  __align__(16) float w2[16 * 12];
+  float b1[16], b3[32];
   float w4[16 * 32], b4[16], w5[2 * 16], b5[2];
   float red_f[16 * 4];
   int red_i[16];
@@ -405,7 +415,11 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
     sm.w3_hi[(tap * 32 + co) * kPixW + cp] = hi;
     sm.w3_lo[(tap * 32 + co) * kPixW + cp] = lo;
   }
-  if (tid < 144) { sm.w1[tid] = w.hid1_w[tid]; sm.w2[tid] = w.hid2_w[tid]; }
+  if (tid < 192) {
+    const int co = tid / 12, k = tid - co * 12;
+    sm.w1[tid] = (k < 9) ? w.hid1_w[co * 9 + k] : 0.f;
+    sm.w2[tid] = (k < 9) ? w.hid2_w[co * 9 + k] : 0.f;
+  }
   if (tid < 16) { sm.b1[tid] = w.hid1_b[tid]; sm.b4[tid] = w.hid4_b[tid]; }
   if (tid < 32) { sm.b3[tid] = w.hid3_b[tid]; sm.w5[tid] = w.occ_w[tid]; }
   if (tid < 2) sm.b5[tid] = w.occ_b[tid];
@@ -451,19 +465,26 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
       for (int e = 0; e < 2; ++e) {
         const int co = 2 * cp + e;
         float a0 = sm.b1[co], a1 = a0;
+        float wk[12];
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+          *reinterpret_cast<float4*>(wk + 4 * v) = reinterpret_cast<const float4*>(sm.w1 + co * 12)[v];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const float wv = sm.w1[co * 9 + ky * 3 + kx];
+            const float wv = wk[ky * 3 + kx];
             a0 = fmaf(win[ky][kx], wv, a0);
             a1 = fmaf(win[ky][kx + 1], wv, a1);
           }
         o[0][e] = fmaxf(a0, 0.f);
         o[1][e] = fmaxf(a1, 0.f);
 #pragma unroll
+        for (int v = 0; v < 3; ++v)
+          *reinterpret_cast<float4*>(wk + 4 * v) = reinterpret_cast<const float4*>(sm.w2 + co * 12)[v];
+#pragma unroll
         for (int k = 0; k < 9; ++k) {
-          const float w2v = sm.w2[co * 9 + k];
+          const float w2v = wk[k];
           st[0][k] = fmaf(o[0][e], w2v, st[0][k]);
           st[1][k] = fmaf(o[1][e], w2v, st[1][k]);
         }
