@@ -1,0 +1,73 @@
+"""Wave model of the GEMM launches of one inference step (no GPU needed).
+
+For every GEMM of the step it replays the tile choice of csrc/gemm_tc.cu (2-SM pair tiles of
+256 x {128,256} over 74 clusters; 1-SM 128 x 64 tiles over 148 CTAs for N = 64) and reports
+tiles, rounds, the wave-quantisation efficiency tiles / (rounds * workers), and the time the
+issued bf16 MMA work would take at the measured cuBLAS peak.  DESIGN.md section 8 quotes it.
+
+  python scripts/tile_model.py [--frames 48 --queries 256] [--peak 1422.8]
+"""
+import argparse
+import math
+
+SMS = 148
+
+
+def choice(m_rows, n, planes):
+  m_tiles = math.ceil(m_rows / 128)
+  if n >= 128 and m_tiles >= 2:
+    half, pr = SMS // 2, (m_tiles + 1) // 2
+    c128 = math.ceil(pr * math.ceil(n / 128) / half) * 128
+    c256 = math.ceil(pr * math.ceil(n / 256) / half) * 256
+    bn = 256 if (n >= 256 and c256 * 9 <= c128 * 10) else 128
+    tiles = pr * math.ceil(n / bn)
+    return f'2SM 256x{bn}', tiles, half
+  bn = 64 if n <= 64 else 128
+  return f'1SM 128x{bn}', m_tiles * math.ceil(n / bn), SMS
+
+
+def step_gemms(frames, queries):
+  g = []
+  hw = {0: 128 * 128, 1: 64 * 64, 2: 32 * 32, 3: 32 * 32}
+  ch = (64, 128, 256, 256)
+  cin = 64
+  for grp in range(4):
+    rows, c = frames * hw[grp], ch[grp]
+    g.append((f'resnet g{grp} proj 1x1', rows, c, max(cin, 64), 2, 1))
+    g.append((f'resnet g{grp} conv_0', rows, c, 9 * cin, 2, 1))
+    g.append((f'resnet g{grp} conv 3x3 x3', rows, c, 9 * c, 2, 3))
+    cin = c
+  rows = frames * 32 * 32
+  g.append(('extra_convs 256->1024', rows, 1024, 9 * 256, 2, 5))
+  g.append(('extra_convs 1024->256', rows, 256, 9 * 1024, 2, 5))
+  g.append(('cost volume (6 MMAs)', frames * 1024, queries, 256, 3, 1))
+  r = queries * frames
+  g.append(('mixer linear_in', r, 512, 576, 2, 4))
+  g.append(('mixer up', r, 2048, 512, 2, 48))
+  g.append(('mixer down', r, 512, 2048, 2, 48))
+  g.append(('mixer linear_out', r, 388, 512, 2, 4))
+  return g
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--frames', type=int, default=48)
+  ap.add_argument('--queries', type=int, default=256)
+  ap.add_argument('--peak', type=float, default=1422.8, help='bf16 TFLOP/s (MEASURED_PEAKS sustained)')
+  a = ap.parse_args()
+  print(f'| GEMM | M x N x K | tile | tiles | rounds | quantisation | launches | MMA-bound ms/step |')
+  print('|---|---|---|---|---|---|---|---|')
+  total = 0.0
+  for name, m, n, k, planes, count in step_gemms(a.frames, a.queries):
+    kind, tiles, workers = choice(m, n, planes)
+    rounds = math.ceil(tiles / workers)
+    eff = tiles / (rounds * workers)
+    terms = planes * (planes + 1) // 2
+    ms = 2.0 * m * n * k * terms / (a.peak * 1e12) * 1e3 * count
+    total += ms
+    print(f'| {name} | {m} x {n} x {k} | {kind} | {tiles} | {rounds} | {eff:.0%} | {count} | {ms:.3f} |')
+  print(f'| total | | | | | | | {total:.2f} |')
+
+
+if __name__ == '__main__':
+  main()

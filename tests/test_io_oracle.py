@@ -67,3 +67,42 @@ def test_tapvid_bad_mode():
     io_oracle.compute_tapvid_metrics(np.zeros((1, 1, 3)), np.zeros((1, 1, 2), bool),
                                      np.zeros((1, 1, 2, 2)), np.zeros((1, 1, 2), bool),
                                      np.zeros((1, 1, 2, 2)), 'last')
+
+
+@pytest.mark.parametrize('trackwise', [False, True])
+def test_product_ratio_logic_matches_reference_from_oracle_counts(tapvid_golden, trackwise):
+  """tapnet_b200.metrics.metrics_from_counts (the host half of the device metrics; runs on CPU
+  tensors too) applied to the oracle's counters reproduces the reference's 13 metrics bit for bit."""
+  from tapnet_b200 import metrics
+  g = tapvid_golden
+  for mode in ('first', 'strided'):
+    counts = io_oracle.tapvid_counts(g['query_points'], g['gt_occluded'], g['gt_tracks'],
+                                     g['pred_occluded'], g['pred_tracks'], mode)
+    assert counts.shape == (3, 9, 18) and counts.dtype == np.int32
+    m = metrics.metrics_from_counts(torch.from_numpy(counts), trackwise)
+    prefix = f'{mode}_{"track" if trackwise else "video"}_'
+    for k, v in m.items():
+      np.testing.assert_array_equal(v.numpy(), g[prefix + k], err_msg=k)
+
+
+def test_counts_are_consistent():
+  """Counter identities that hold for any input: tp <= correct <= visible <= evaluated, etc."""
+  rng = np.random.default_rng(8)
+  B, N, T = 2, 5, 17
+  qp = np.zeros((B, N, 3), np.float32)
+  qp[..., 0] = rng.integers(0, T, (B, N))
+  gt = rng.uniform(0, 64, (B, N, T, 2)).astype(np.float32)
+  pred = (gt + rng.normal(0, 4, gt.shape)).astype(np.float32)
+  go, po = rng.uniform(size=(B, N, T)) < 0.5, rng.uniform(size=(B, N, T)) < 0.5
+  for mode in ('first', 'strided'):
+    c = io_oracle.tapvid_counts(qp, go, gt, po, pred, mode).astype(np.int64)
+    assert (c[..., 1] <= c[..., 0]).all() and (c[..., 2] <= c[..., 0]).all()
+    for i in range(5):
+      assert (c[..., 8 + i] <= c[..., 3 + i]).all() and (c[..., 3 + i] <= c[..., 2]).all()
+      if i:
+        assert (c[..., 3 + i] >= c[..., 2 + i]).all()      # wider threshold, more points inside
+        assert (c[..., 13 + i] <= c[..., 12 + i]).all()    # ... and fewer false positives
+    if mode == 'strided':
+      assert (c[..., 0] == T - 1).all()
+    else:
+      assert (c[..., 0] == T - 1 - np.round(qp[..., 0]).astype(np.int64)).all()
