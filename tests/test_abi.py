@@ -52,3 +52,39 @@ def test_struct_sizes_match_header():
   assert ctypes.sizeof(_lib.MixerIO) == 8 + 8 + 16 + 32 + 8 + 8
   assert ctypes.sizeof(_lib.CorrArgs) == 72 + 24 + 24 + 48 + 24
   assert ctypes.sizeof(_lib.UpdateArgs) == 8 + 40 + 48 + 7 * 8
+
+
+def test_header_is_plain_c_and_ctypes_mirror_matches_the_compiler(tmp_path):
+  """include/tapir_b200.h compiles as C99 (no C++ / torch types in the boundary) and every
+  ctypes Structure has the size AND field offsets the C compiler gives the header's struct."""
+  import shutil
+  import subprocess
+  import pytest
+  gcc = shutil.which('gcc')
+  if gcc is None:
+    pytest.skip('no gcc')
+  pairs = [('tapir_linear', _lib.Linear), ('tapir_resnet_block', _lib.ResnetBlock),
+           ('tapir_extra_block', _lib.ExtraBlock), ('tapir_backbone_weights', _lib.BackboneWeights),
+           ('tapir_head_weights', _lib.HeadWeights), ('tapir_mixer_block', _lib.MixerBlock),
+           ('tapir_mixer_weights', _lib.MixerWeights), ('tapir_mixer_io', _lib.MixerIO),
+           ('tapir_corr_level', _lib.CorrLevel), ('tapir_corr_args', _lib.CorrArgs),
+           ('tapir_update_args', _lib.UpdateArgs), ('tapir_tapvid_args', _lib.TapvidArgs)]
+  lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tapir_b200.h"', 'int main(void) {']
+  for cname, cls in pairs:
+    lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+    for fname, _ in cls._fields_:
+      lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+    lines.append('  printf("\\n");')
+  lines += ['  return 0;', '}']
+  src = tmp_path / 'abi_probe.c'
+  src.write_text('\n'.join(lines))
+  exe = tmp_path / 'abi_probe'
+  subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'),
+                  str(src), '-o', str(exe)], check=True)
+  out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+  assert len(out) == len(pairs)
+  for line, (cname, cls) in zip(out, pairs):
+    name, size, *offs = line.split()
+    assert name == cname
+    assert int(size) == ctypes.sizeof(cls), cname
+    assert [int(o) for o in offs] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
