@@ -88,3 +88,28 @@ def test_header_is_plain_c_and_ctypes_mirror_matches_the_compiler(tmp_path):
     assert name == cname
     assert int(size) == ctypes.sizeof(cls), cname
     assert [int(o) for o in offs] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
+
+
+def test_c_host_example_links_and_fails_loudly_without_a_gpu(tmp_path):
+  """examples/c_host.c (plain C99, links the .so directly) builds and runs: version and size
+  queries work without a GPU; a compute call returns a status + message instead of crashing."""
+  import shutil
+  import subprocess
+  import pytest
+  import torch
+  gcc = shutil.which('gcc')
+  if gcc is None:
+    pytest.skip('no gcc')
+  _lib.load()  # the library must have been built
+  libdir = os.path.dirname(_lib.LIB_PATH)
+  exe = tmp_path / 'c_host'
+  subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'),
+                  os.path.join(ROOT, 'examples', 'c_host.c'), '-L', libdir, '-ltapir_b200',
+                  f'-Wl,-rpath,{libdir}', '-o', str(exe)], check=True)
+  out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, timeout=120).stdout
+  lines = dict(l.split(' ', 1) for l in out.strip().splitlines())
+  assert lines['abi'] == '1'
+  assert int(lines['backbone_ws']) > 1 << 30 and int(lines['mixer_ws']) > 0
+  assert lines['bad_args'].startswith('rc=1 ') and 'bad arguments' in lines['bad_args']
+  if not torch.cuda.is_available():
+    assert lines['host_pointers'].startswith('rc=3 ') and 'CUDA error' in lines['host_pointers']
