@@ -130,7 +130,7 @@ class ClockSampler:
 
 
 def build_inputs(world):
-  from oracle import synth  # test infrastructure: only used to generate the seeded inputs
+  from tapnet_b200 import synth  # seeded synthetic inputs
   video = synth.make_video(T_FRAMES, RES, RES, seed=1)
   queries = synth.make_queries(Q_PER_GPU * world, T_FRAMES, RES, RES, seed=2)
   sd = synth.make_state_dict(0)

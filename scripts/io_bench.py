@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import synth  # noqa: E402  (seeded weights only)
+from tapnet_b200 import synth  # noqa: E402  (seeded weights)
 from tapnet_b200 import bulk, live, metrics, tapir_model  # noqa: E402
 
 

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from oracle import synth  # noqa: E402
+from tapnet_b200 import synth  # noqa: E402
 from tapnet_b200 import tapir_model  # noqa: E402
 
 ap = argparse.ArgumentParser()
