@@ -324,11 +324,16 @@ constexpr int kPixW = 9;                       // 32-bit words per pixel: 16 bf1
 constexpr int kPlaneWords = kOccPlane * kPixW; // 35 x 35 pixels
 constexpr int kTapW = (kG + 2) * (kG + 2);
 
+// W3S = 32-bit words per hid3 weight row.  9 (the validated default) shares the pixel stride and
+// makes every weight-fragment load of phase D 2-way bank conflicted (lane group g = 7 lands on the
+// banks of g = 0); 12 makes {12 g + tq} distinct mod 32 (opt-in TAPIR_B200_HEAD_W3S=12 until it
+// has run on a GPU; profiles/r01_ncu_summary.md).
+template <int W3S>
 struct HeadTcSmem {
   float cv[kTapW];
   float stap[9 * kTapW];
   uint32_t occ_hi[kPlaneWords], occ_lo[kPlaneWords];
-  uint32_t w3_hi[9 * 32 * kPixW], w3_lo[9 * 32 * kPixW];  // [tap][co][ci pairs]
+  uint32_t w3_hi[9 * 32 * W3S], w3_lo[9 * 32 * W3S];  // [tap][co][ci pairs]
   // hid1 / hid2 weights, 9 taps padded to 12 per channel: three broadcast LDS.128 per channel
   __align__(16) float w1[16 * 12];
   __align__(16) float w2[16 * 12];
@@ -392,13 +397,14 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+template <int W3S>
 __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
     const tapir_head_weights w, const float* __restrict__ cost_volume, int T, int num_maps,
     const float* __restrict__ query_tyx, float temperature, int init_h, int init_w,
     float* __restrict__ points, float* __restrict__ occ_out, float* __restrict__ expd_out,
     int* __restrict__ argmax_out) {
   extern __shared__ __align__(16) uint8_t head_tc_smem_raw[];
-  HeadTcSmem& sm = *reinterpret_cast<HeadTcSmem*>(head_tc_smem_raw);
+  HeadTcSmem<W3S>& sm = *reinterpret_cast<HeadTcSmem<W3S>*>(head_tc_smem_raw);
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
@@ -412,8 +418,8 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
     float v0 = w.hid3_w[(co * 16 + 2 * cp) * 9 + tap], v1 = w.hid3_w[(co * 16 + 2 * cp + 1) * 9 + tap];
     const uint32_t hi = bf16x2_split(v0, v1);
     const uint32_t lo = bf16x2_split(v0, v1);
-    sm.w3_hi[(tap * 32 + co) * kPixW + cp] = hi;
-    sm.w3_lo[(tap * 32 + co) * kPixW + cp] = lo;
+    sm.w3_hi[(tap * 32 + co) * W3S + cp] = hi;
+    sm.w3_lo[(tap * 32 + co) * W3S + cp] = lo;
   }
   if (tid < 192) {
     const int co = tid / 12, k = tid - co * 12;
@@ -572,7 +578,7 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
       al[2] = sm.occ_lo[pa + tq + 4]; al[3] = sm.occ_lo[pb + tq + 4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const int wb = (tap * 32 + nt * 8 + g) * kPixW + tq;
+        const int wb = (tap * 32 + nt * 8 + g) * W3S + tq;
         uint32_t bh[2] = {sm.w3_hi[wb], sm.w3_hi[wb + 4]};
         uint32_t bl[2] = {sm.w3_lo[wb], sm.w3_lo[wb + 4]};
         mma_bf16_16816(acc[nt], al, bh);
@@ -647,13 +653,18 @@ int cost_volume_head(const tapir_head_weights* w, const float* cost_volume, int 
                      const float* query_tyx, float temperature, int init_h, int init_w,
                      float* points, float* occ, float* expd, int* argmax, cudaStream_t s) {
   static int use_simt = -1;
+  static int w3_stride = 9;
   if (use_simt < 0) {
     const char* e = getenv("TAPIR_B200_HEAD");
     use_simt = (e != nullptr && strcmp(e, "simt") == 0) ? 1 : 0;
     TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(HeadSmem)));
-    TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(HeadTcSmem)));
+    TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(HeadTcSmem<9>)));
+    TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_tc_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(HeadTcSmem<12>)));
+    const char* ws = getenv("TAPIR_B200_HEAD_W3S");
+    w3_stride = (ws != nullptr && atoi(ws) == 12) ? 12 : 9;
   }
   TAPIR_CHECK_ARG(N <= 65535, "cost_volume_head: at most 65535 queries per call (got %d)", N);
   // head = 2,950,208 FLOP per (n,t); 4 KB map in, 16 B out
@@ -665,9 +676,13 @@ int cost_volume_head(const tapir_head_weights* w, const float* cost_volume, int 
   } else {
     const int maps = N * T;
     const int ctas = maps < num_sms() ? maps : num_sms();
-    cost_volume_head_tc_kernel<<<ctas, kHT, sizeof(HeadTcSmem), s>>>(*w, cost_volume, T, maps, query_tyx,
-                                                                    temperature, init_h, init_w, points,
-                                                                    occ, expd, argmax);
+    if (w3_stride == 12) {
+      cost_volume_head_tc_kernel<12><<<ctas, kHT, sizeof(HeadTcSmem<12>), s>>>(
+          *w, cost_volume, T, maps, query_tyx, temperature, init_h, init_w, points, occ, expd, argmax);
+    } else {
+      cost_volume_head_tc_kernel<9><<<ctas, kHT, sizeof(HeadTcSmem<9>), s>>>(
+          *w, cost_volume, T, maps, query_tyx, temperature, init_h, init_w, points, occ, expd, argmax);
+    }
   }
   count_launch();
   TAPIR_LAUNCH_CHECK("cost_volume_head_kernel");
