@@ -397,6 +397,9 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+static_assert(sizeof(HeadTcSmem<9>) <= 227 * 1024 && sizeof(HeadTcSmem<12>) <= 227 * 1024,
+              "head kernel shared memory exceeds the 227 KB opt-in limit");
+
 template <int W3S>
 __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
     const tapir_head_weights w, const float* __restrict__ cost_volume, int T, int num_maps,
