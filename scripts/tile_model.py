@@ -49,12 +49,62 @@ def step_gemms(frames, queries):
   return g
 
 
+# wave-model row -> key of bench.py's kernel_breakdown
+_CLASS = {'proj': 'backbone.proj', 'resnet': 'backbone.conv', 'extra_convs': 'backbone.extra_conv',
+          'cost volume': 'cost_volume.gemm', 'linear_in': 'mixer.linear_in', 'mixer up': 'mixer.up',
+          'mixer down': 'mixer.down', 'linear_out': 'mixer.linear_out'}
+
+
+def _class_of(name):
+  for k in ('proj', 'extra_convs', 'cost volume', 'linear_in', 'mixer up', 'mixer down', 'linear_out',
+            'resnet'):
+    if k in name:
+      return _CLASS[k]
+  return None
+
+
+def compare(bench_json, frames, queries, peak, chunks=1):
+  """Per GEMM class: measured ms (bench.py kernel_breakdown) against the MMA-bound time at the
+  cuBLAS peak and against that time divided by the wave-quantisation efficiency."""
+  import json
+  with open(bench_json) as fh:
+    line = [l for l in fh if l.startswith('{')][-1]
+  kb = json.loads(line)['kernel_breakdown']
+  agg = {}
+  for name, m, n, k, planes, count in step_gemms(frames, queries):
+    kind, tiles, workers = choice(m, n, planes)
+    rounds = math.ceil(tiles / workers)
+    eff = tiles / (rounds * workers)
+    terms = planes * (planes + 1) // 2
+    ms = 2.0 * m * n * k * terms / (peak * 1e12) * 1e3 * count
+    c = _class_of(name)
+    if c.startswith('mixer') or c.startswith('cost_volume'):
+      ms *= chunks  # the host runs the query-dependent stages once per chunk of queries
+    a = agg.setdefault(c, [0.0, 0.0])
+    a[0] += ms
+    a[1] += ms / eff
+  print('| class | measured ms | MMA-bound ms | quantisation-bound ms | measured / quantisation-bound |')
+  print('|---|---|---|---|---|')
+  tm = tb = tq = 0.0
+  for c, (ms, msq) in agg.items():
+    meas = kb[c]['ms_per_step']
+    tm, tb, tq = tm + meas, tb + ms, tq + msq
+    print(f'| {c} | {meas:.3f} | {ms:.3f} | {msq:.3f} | {meas / msq:.2f} |')
+  print(f'| all GEMMs | {tm:.2f} | {tb:.2f} | {tq:.2f} | {tm / tq:.2f} |')
+
+
 def main():
   ap = argparse.ArgumentParser()
+  ap.add_argument('--bench', help='bench.py JSON line to compare the model with')
+  ap.add_argument('--chunks', type=int, default=1,
+                  help='query chunks per step (--queries is then the chunk size)')
   ap.add_argument('--frames', type=int, default=48)
   ap.add_argument('--queries', type=int, default=256)
   ap.add_argument('--peak', type=float, default=1422.8, help='bf16 TFLOP/s (MEASURED_PEAKS sustained)')
   a = ap.parse_args()
+  if a.bench:
+    compare(a.bench, a.frames, a.queries, a.peak, a.chunks)
+    return
   print(f'| GEMM | M x N x K | tile | tiles | rounds | quantisation | launches | MMA-bound ms/step |')
   print('|---|---|---|---|---|---|---|---|')
   total = 0.0
