@@ -16,7 +16,8 @@ TRACK_TOL = 5e-4
 LOGIT_TOL = 5e-5
 
 OFFLINE = ['c1_bootstapir_256x8_n16', 'tapir_pl0_noextra_256x4_n8', 'bootstapir_320x384x4_n12',
-           'causal_256x6_n16']
+           'causal_256x6_n16', 'causal_480x3_n8']
+CAUSAL = ['causal_256x6_n16', 'causal_480x3_n8']   # the second: live-demo shape, two levels
 
 
 def _setup(g):
@@ -57,8 +58,9 @@ def test_oracle_matches_reference_golden(name):
   np.testing.assert_allclose(mean_tracks, g['tracks'], atol=TRACK_TOL)
 
 
-def test_oracle_streaming_matches_reference_golden():
-  g = load_golden('causal_256x6_n16')
+@pytest.mark.parametrize('name', CAUSAL)
+def test_oracle_streaming_matches_reference_golden(name):
+  g = load_golden(name)
   cfg, sd, video, q = _setup(g)
   m = g['meta']
   with torch.no_grad():
