@@ -75,6 +75,43 @@ def test_streaming_matches_reference_golden():
   assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_e < LOGIT_TOL and e_s < 5e-4
 
 
+@pytest.mark.skipif(__import__('os').environ.get('TAPIR_B200_EXPERIMENTAL') != '1',
+                    reason='added after the round-1 GPU budget ended: run once with '
+                           'TAPIR_B200_EXPERIMENTAL=1 (scripts/gpu_ci.sh experimental), then enable')
+def test_live_demo_shape_480_two_levels_experimental():
+  """The README's live-demo shape (480x480, 8 points, refinement levels 256 + 480 = 8 iterations):
+  offline-causal forward and per-frame streaming against the reference's golden outputs."""
+  g = load_golden('causal_480x3_n8')
+  meta = g['meta']
+  model, _, _ = get_model(causal=True)
+  video, q = _inputs(meta)
+  video, q = video.cuda(), q.cuda()
+  out = model(video, q)
+  e_t = np.abs(out['tracks'][0].cpu().numpy() - g['tracks']).max()
+  e_o = np.abs(out['occlusion'][0].cpu().numpy() - g['occlusion']).max()
+  e_e = np.abs(out['expected_dist'][0].cpu().numpy() - g['expected_dist']).max()
+  assert len(out['unrefined_tracks']) == 8
+  assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_e < LOGIT_TOL
+  g0 = model.get_feature_grids(video[:, :1], False)
+  qf0 = model.get_query_features(video[:, :1], False, q, g0)
+  assert len(qf0.resolutions) == 3
+  state = [{k: v.cuda() for k, v in d.items()}
+           for d in model.construct_initial_causal_state(meta['N'], len(qf0.resolutions) - 1)]
+  tr, oc = [], []
+  for t in range(meta['T']):
+    gr = model.get_feature_grids(video[:, t:t + 1], False)
+    r = model.estimate_trajectories((meta['H'], meta['W']), False, gr, qf0, None, 64,
+                                    causal_context=state, get_causal_context=True)
+    state = r['causal_context']
+    tr.append(r['tracks'][-1][0].cpu().numpy())
+    oc.append(r['occlusion'][-1][0].cpu().numpy())
+  e_t = np.abs(np.concatenate(tr, 1) - g['online_tracks']).max()
+  e_o = np.abs(np.concatenate(oc, 1) - g['online_occlusion']).max()
+  e_s = np.abs(state[-1]['block_11_causal_2'][0, :, :, ::64].cpu().numpy() - g['online_state_sub']).max()
+  U.record('e2e_live_demo_480', tracks_err=e_t, occ_err=e_o, state_err=e_s)
+  assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_s < 5e-4
+
+
 def test_chunking_and_oracle_agreement_larger():
   """T=12, N=96 against the CPU oracle (a size the oracle finishes in seconds)."""
   model, sd, cfg = get_model()
