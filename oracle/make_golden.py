@@ -24,6 +24,8 @@ CASES = {
     'bootstapir_320x384x4_n12': (dict(pyramid_level=1), 4, 12, 320, 384, 'offline'),
     'causal_256x6_n16': (dict(pyramid_level=1, use_casual_conv=True), 6, 16, 256, 256,
                          'causal'),
+    # BASELINE config 5's pyramid: 1024x1024 -> levels 256 / 512 / 1024, 12 refinement iterations
+    'bootstapir_1024x2_n6': (dict(pyramid_level=1), 2, 6, 1024, 1024, 'offline'),
     # the README's live-demo shape (17 fps figure): 480x480, 8 points, two levels = 8 iterations
     'causal_480x3_n8': (dict(pyramid_level=1, use_casual_conv=True), 3, 8, 480, 480, 'causal'),
 }
