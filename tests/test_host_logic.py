@@ -66,3 +66,47 @@ def test_default_resolutions():
   assert f((256, 256), (256, 256)) == [(256, 256)]
   assert f((480, 480), (256, 256)) == [(256, 256), (480, 480)]
   assert f((1024, 1024), (256, 256)) == [(256, 256), (512, 512), (1024, 1024)]
+
+
+def test_default_resolutions_sweep_matches_reference_and_oracle():
+  """generate_default_resolutions over a sweep of frame sizes: product == oracle restatement, and
+  == the reference's own function when it is mounted (utils.py:275-317)."""
+  import contextlib
+  import io
+  from oracle import reference_loader
+  from oracle import tapir_oracle as O
+  ref = None
+  if reference_loader.available():
+    reference_loader.load()
+    from tapnet.torch import utils as ref_utils  # pylint: disable=g-import-not-at-top
+    ref = ref_utils.generate_default_resolutions
+  sizes = [(256, 256), (240, 240), (480, 480), (480, 640), (360, 640), (512, 512), (720, 1280),
+           (1024, 1024), (1080, 1920), (264, 264), (250, 500), (2048, 1024)]
+  for hw in sizes:
+    with contextlib.redirect_stdout(io.StringIO()):   # the non-multiple-of-8 warning
+      got = tapir_model.generate_default_resolutions(hw, (256, 256))
+      want = O.default_resolutions(hw, (256, 256))
+      assert [tuple(r) for r in got] == [tuple(r) for r in want], hw
+      if ref is not None:
+        assert [tuple(r) for r in got] == [tuple(int(v) for v in r) for r in ref(hw, (256, 256))], hw
+    assert all(r[0] % 8 == 0 and r[1] % 8 == 0 for r in got)
+    assert tuple(got[0]) == (256, 256)
+
+
+def test_live_crop_window_matches_reference_slicing():
+  """live.center_square_window == the slicing of get_frame (pytorch_live_demo.py:88-95) on a
+  coordinate image, for landscape / portrait / square frames."""
+  import numpy as np
+  from tapnet_b200 import live
+  for h, w in [(240, 320), (320, 240), (480, 480), (36, 53), (1080, 1920), (7, 3)]:
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing='ij')
+    image = np.stack([yy, xx], -1)
+    trunc = abs(w - h) // 2
+    if w > h:
+      want = image[:, trunc:-trunc]
+    elif w < h:
+      want = image[trunc:-trunc]
+    else:
+      want = image
+    y0, x0, ch, cw = live.center_square_window(h, w)
+    np.testing.assert_array_equal(image[y0:y0 + ch, x0:x0 + cw], want)
