@@ -28,11 +28,45 @@ CASES = {
     'bootstapir_1024x2_n6': (dict(pyramid_level=1), 2, 6, 1024, 1024, 'offline'),
     # the README's live-demo shape (17 fps figure): 480x480, 8 points, two levels = 8 iterations
     'causal_480x3_n8': (dict(pyramid_level=1, use_casual_conv=True), 3, 8, 480, 480, 'causal'),
+    # constructor argument initial_resolution (tapir_model.py:86): a 24 x 40 cost-volume map
+    'bootstapir_ir192x320x3_n10': (dict(pyramid_level=1, initial_resolution=(192, 320)), 3, 10, 192,
+                                   320, 'offline'),
 }
 
 
 def _np(x):
   return x.detach().cpu().numpy()
+
+
+class _StageAProbe:
+  """Records what `utils.soft_argmax_heatmap_batched` (utils.py:116-150) sees and decides: wraps
+  the reference function, repeats its own arg-max expression on the same tensor (same op, same
+  input -> same indices) and passes the call through unchanged."""
+
+  def __init__(self):
+    self.argmax, self.margin = [], []
+
+  def __enter__(self):
+    from tapnet.torch import utils as ref_utils  # the unmodified reference module
+    self._mod = ref_utils
+    self._orig = ref_utils.soft_argmax_heatmap_batched
+
+    def wrapped(softmax_val, threshold=5):
+      b, n, t = softmax_val.shape[:3]
+      flat = softmax_val.reshape(b, n, t, -1)
+      self.argmax.append(torch.argmax(flat, dim=-1)[0])
+      top2 = torch.topk(flat, 2, dim=-1).values[0]
+      self.margin.append(top2[..., 0] - top2[..., 1])
+      return self._orig(softmax_val, threshold)
+
+    ref_utils.soft_argmax_heatmap_batched = wrapped
+    return self
+
+  def __exit__(self, *exc):
+    self._mod.soft_argmax_heatmap_batched = self._orig
+
+  def result(self):
+    return torch.cat(self.argmax, dim=0), torch.cat(self.margin, dim=0)
 
 
 def run_case(name):
@@ -54,8 +88,18 @@ def run_case(name):
     out['qfeat_hires'] = _np(qf.hires[-1][0, :, ::8])
     meta['resolutions'] = [list(map(int, r)) for r in grids.resolutions]
     torch.manual_seed(123)  # estimate_trajectories shuffles queries with torch.randperm
-    tr = model.estimate_trajectories(video.shape[-3:-1], False, grids, qf, queries,
-                                     query_chunk_size=64)
+    perm = torch.randperm(N)  # the permutation the call below will draw (tapir_model.py:464)
+    torch.manual_seed(123)
+    with _StageAProbe() as probe:
+      tr = model.estimate_trajectories(video.shape[-3:-1], False, grids, qf, queries,
+                                       query_chunk_size=64)
+    # stage-A arg-max cell of every (query, frame) heat map, exactly as the reference computed it
+    # (utils.py:126), un-permuted to query order; plus the top-2 probability margin of each map
+    am, mg = probe.result()
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(N)
+    out['stage_a_argmax'] = _np(am[inv]).astype(np.int32)
+    out['stage_a_margin'] = _np(mg[inv]).astype(np.float32)
     out['tracks_iters'] = np.stack([_np(t[0]) for t in tr['tracks']])
     out['occlusion_iters'] = np.stack([_np(t[0]) for t in tr['occlusion']])
     out['expected_dist_iters'] = np.stack([_np(t[0]) for t in tr['expected_dist']])
@@ -87,8 +131,9 @@ def run_case(name):
 
 
 def main():
+  import sys  # pylint: disable=g-import-not-at-top
   os.makedirs(GOLDEN_DIR, exist_ok=True)
-  for name in CASES:
+  for name in (sys.argv[1:] or CASES):
     out = run_case(name)
     path = os.path.join(GOLDEN_DIR, name + '.npz')
     np.savez_compressed(path, **out)

@@ -378,11 +378,11 @@ int stem_conv(const void* video, int video_u8, const float* w_packed, int frames
               float* out, cudaStream_t s) {
   TAPIR_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "stem_conv: H, W must be even");
   const int smem = (147 * 64 + kStemPatchY * kStemPatchX * 3) * (int)sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.pending()) {
     TAPIR_CUDA(cudaFuncSetAttribute(stem_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     TAPIR_CUDA(cudaFuncSetAttribute(stem_conv_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.mark();
   }
   ProfileScope ps("backbone.stem_conv", s, 2.0 * frames * (H / 2) * (W / 2) * 64 * 147,
                   (double)frames * H * W * 3 * (video_u8 ? 1 : 4) +

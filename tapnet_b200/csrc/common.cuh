@@ -49,7 +49,18 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_s != 0) return _s;          \
   } while (0)
 
-int num_sms();
+int num_sms();  // of the CURRENT device
+
+// Per-device one-time setup (cudaFuncSetAttribute, scratch allocations): every cache in this
+// library is keyed by cudaGetDevice(), so several GPUs can be driven from one process.
+constexpr int kMaxDevices = 64;
+int current_device();  // cudaGetDevice(), clamped to [0, kMaxDevices)
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  // true exactly once per device; call mark() after the setup succeeded
+  bool pending() const { return !done[current_device()]; }
+  void mark() { done[current_device()] = true; }
+};
 
 // counts kernels launched by this library (bench.py reports it as gpu_launches)
 extern unsigned long long g_launch_count;

@@ -769,12 +769,13 @@ int encode_bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
 }
 
 int* device_error_flag() {
-  static int* flag = nullptr;
-  if (flag == nullptr) {
-    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(flag, 0, sizeof(int));
+  static int* flag[kMaxDevices] = {};
+  const int dev = current_device();
+  if (flag[dev] == nullptr) {
+    if (cudaMalloc(&flag[dev], sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(flag[dev], 0, sizeof(int));
   }
-  return flag;
+  return flag[dev];
 }
 
 void choose_conv_tile(int H, int W, int* tw, int* th) {
@@ -801,13 +802,13 @@ bool use_cluster() {
 template <int BLOCK_N, int P>
 int launch(const TcParams& p, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = TcCfg<BLOCK_N, P>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.pending()) {
     TAPIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, P, false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     TAPIR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, P, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured.mark();
   }
   const double kl = g.k_logical > 0 ? g.k_logical : g.K;
   const double out_b = (g.out_f32 ? 4.0 : 0.0) + (g.out_planes ? 2.0 * g.out_P : 0.0) + (g.residual ? 4.0 : 0.0);
@@ -856,11 +857,11 @@ int use_2sm() {
 template <int BN, int P>
 int launch2(const TcParams& p, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = Tc2Cfg<BN, P>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.pending()) {
     TAPIR_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
-    configured = true;
+    configured.mark();
   }
   const double kl = g.k_logical > 0 ? g.k_logical : g.K;
   const double out_b = (g.out_f32 ? 4.0 : 0.0) + (g.out_planes ? 2.0 * g.out_P : 0.0) + (g.residual ? 4.0 : 0.0);

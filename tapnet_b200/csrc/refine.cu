@@ -125,9 +125,45 @@ __global__ void __launch_bounds__(96) local_corr_kernel(const CorrParams p) {
     const int x0 = (int)floorf(pix(cx, -3, gw));
     const int x_last = (int)floorf(pix(cx, 3, gw)) + 1;
     int box_w = x_last - x0 + 1;
-    if (box_w > kBoxColsMax) box_w = kBoxColsMax;  // host guarantees gw/gh <= 2 (see local_corr)
     if (box_w < 2) box_w = 2;
     const float* frame = L.grid + (long long)t * gh * gw * L.C;
+    if (box_w > kBoxColsMax) {
+      // Wide grids (w/h > 2: the reference spaces the 49 samples gw/gh cells apart in x because it
+      // normalises x by h, utils.py:104): the samples' cells no longer fit the 8 x 16 box, so
+      // every sample is taken directly - 4 corner dot products each.  Same arithmetic, slower;
+      // only panoramic aspect ratios come here.
+      float4 q[2];
+      const int V = L.C / 128;
+      const float* qsrc = (L.C == 128) ? fhi : flo;
+      q[0] = reinterpret_cast<const float4*>(qsrc)[lane];
+      q[1] = (V == 2) ? reinterpret_cast<const float4*>(qsrc)[32 + lane] : make_float4(0, 0, 0, 0);
+      for (int sidx = 0; sidx < 49; ++sidx) {
+        const int dy = sidx / 7 - 3, dx = sidx % 7 - 3;
+        const float iy = pix(cy, dy, gh), ix = pix(cx, dx, gw);
+        const float fy0 = floorf(iy), fx0 = floorf(ix);
+        const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+        const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
+        float v = 0.f;
+#pragma unroll
+        for (int cr = 0; cr < 4; ++cr) {
+          const int yy = (int)fy0 + (cr >> 1), xx = (int)fx0 + (cr & 1);
+          float acc = 0.f;
+          if (yy >= 0 && yy < gh && xx >= 0 && xx < gw) {
+            const float4* cp = reinterpret_cast<const float4*>(frame + ((long long)yy * gw + xx) * L.C);
+            for (int vv = 0; vv < V; ++vv) {
+              const float4 f = __ldg(cp + vv * 32 + lane);
+              acc = fmaf(f.x, q[vv].x, acc);
+              acc = fmaf(f.y, q[vv].y, acc);
+              acc = fmaf(f.z, q[vv].z, acc);
+              acc = fmaf(f.w, q[vv].w, acc);
+            }
+          }
+          acc = warp_sum(acc);
+          v += acc * (((cr & 1) ? wx1 : wx0) * ((cr >> 1) ? wy1 : wy0));
+        }
+        if (lane == 0) corr[warp * 49 + sidx] = v;
+      }
+    } else {
     if (L.C == 128) {
       float4 q[1];
       q[0] = reinterpret_cast<const float4*>(fhi)[lane];
@@ -157,6 +193,7 @@ __global__ void __launch_bounds__(96) local_corr_kernel(const CorrParams p) {
                       cell(ry + 1, rx) * (wx0 * wy1) + cell(ry + 1, rx + 1) * (wx1 * wy1);
       corr[warp * 49 + sidx] = v;
     }
+    }  // box fits
   }
   __syncthreads();
 
@@ -301,16 +338,10 @@ __device__ __forceinline__ void dw_frames(const DwParams& p, const DwWeights& k,
     // written before the rows are recycled for z
     for (int t = max(t0, T - 2); t < t1; ++t)
       p.ctx1_out[((long long)n * 2 + (t - (T - 2))) * 512 + c] = yq[(t - lo) * 512];
-    if (T == 1 && t0 == 0) {  // clip shorter than the context: slot 0 <- old frame -1
-      p.ctx1_out[((long long)n * 2) * 512 + c] =
-          (p.ctx1_in != nullptr) ? p.ctx1_in[((long long)n * 2 + 1) * 512 + c] : 0.f;
-      if (p.ctx2_out != nullptr) {
-        float4 v = make_float4(0, 0, 0, 0);
-        if (p.ctx2_in != nullptr)
-          v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + 1) * 2048 + 4 * c);
-        *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2) * 2048 + 4 * c) = v;
-      }
-    }
+    // clip shorter than the context: slot 0 <- old frame -1, which phase 1 staged in row 3
+    // (frame -1) of this query; reading the staged copy (not ctx1_in) keeps the update correct
+    // when the caller passes the SAME buffers as context in and out (streaming, T = 1)
+    if (T == 1 && t0 == 0) p.ctx1_out[((long long)n * 2) * 512 + c] = yq[3 * 512];
   }
   float y0 = yq[0], y1 = yq[512];
   float ha[4], hb[4], hc[4];
@@ -352,6 +383,11 @@ __device__ __forceinline__ void dw_frames(const DwParams& p, const DwWeights& k,
   };
   h1(0, ha);
   h1(1, hb);
+  // T = 1: hb is h1 of frame -1 (old context slot 1, or zero); it becomes slot 0 of the new
+  // context.  Written only now, after both old slots were read (in/out buffers may alias).
+  if (CAUSAL && p.ctx2_out != nullptr && T == 1 && t0 == 0)
+    *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2) * 2048 + 4 * c) =
+        make_float4(hb[0], hb[1], hb[2], hb[3]);
   const int nout = t1 - t0;
   // output frames whose newest h1 frame (first + i + 2) needs no end-of-sequence handling
   int i_lo = max(0, -(first + 2));
@@ -475,16 +511,8 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
       // written before the rows are recycled for z
       for (int t = max(t0, T - 2); t < t1; ++t)
         p.ctx1_out[((long long)n * 2 + (t - (T - 2))) * 512 + c] = yq[(t - lo) * 512];
-      if (T == 1 && t0 == 0) {  // clip shorter than the context: slot 0 <- old frame -1
-        p.ctx1_out[((long long)n * 2) * 512 + c] =
-            (p.ctx1_in != nullptr) ? p.ctx1_in[((long long)n * 2 + 1) * 512 + c] : 0.f;
-        if (p.ctx2_out != nullptr) {
-          float4 v = make_float4(0, 0, 0, 0);
-          if (p.ctx2_in != nullptr)
-            v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + 1) * 2048 + 4 * c);
-          *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2) * 2048 + 4 * c) = v;
-        }
-      }
+      // clip shorter than the context: slot 0 <- old frame -1 = staged row 3 (see dw_frames)
+      if (T == 1 && t0 == 0) p.ctx1_out[((long long)n * 2) * 512 + c] = yq[3 * 512];
     }
     float y0 = yq[0], y1 = yq[512];
     float ha[4], hb[4], hc[4];
@@ -526,6 +554,9 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
     };
     h1(0, ha);
     h1(1, hb);
+    if (CAUSAL && p.ctx2_out != nullptr && T == 1 && t0 == 0)  // see dw_frames
+      *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2) * 2048 + 4 * c) =
+          make_float4(hb[0], hb[1], hb[2], hb[3]);
     const int nout = t1 - t0;
     // output frames whose newest h1 frame (first + i + 2) needs no end-of-sequence handling
     int i_lo = max(0, -(first + 2));
@@ -736,8 +767,8 @@ int local_corr(const tapir_corr_args* a, cudaStream_t s) {
     const tapir_corr_level& L = a->levels[l];
     TAPIR_CHECK_ARG(L.grid != nullptr && (L.C == 128 || L.C == 256), "local_corr: level %d C=%d unsupported", l, L.C);
     TAPIR_CHECK_ARG((l == 0) == (L.C == 128), "local_corr: level 0 must be the 128-ch hires grid, others 256-ch");
-    // x spacing of the 49 samples is gw/gh cells (reference quirk); the cell box holds 16 columns
-    TAPIR_CHECK_ARG(7.0 * L.w / L.h + 2.0 <= kBoxColsMax, "local_corr: aspect ratio w/h=%d/%d too wide", L.w, L.h);
+    // (x spacing of the 49 samples is gw/gh cells - a reference quirk; boxes wider than the
+    // 16-column table take the per-sample path inside the kernel)
   }
   CorrParams p;
   p.a = *a;
@@ -833,8 +864,8 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     set_error("mixer_forward: workspace too small (%zu < %zu)", ws_bytes, arena.off);
     return kWorkspaceTooSmall;
   }
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.pending()) {
     const int max_smem = kDwRowBudget * 512 * (int)sizeof(float);
     TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -842,7 +873,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
       TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwPipeSmem));
       TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwPipeSmem));
     }
-    configured = true;
+    configured.mark();
   }
   {  // nets.py:235 linear
     GemmArgs g = lin(w->linear);

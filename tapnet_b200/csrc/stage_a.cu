@@ -324,10 +324,11 @@ constexpr int kPixW = 9;                       // 32-bit words per pixel: 16 bf1
 constexpr int kPlaneWords = kOccPlane * kPixW; // 35 x 35 pixels
 constexpr int kTapW = (kG + 2) * (kG + 2);
 
-// W3S = 32-bit words per hid3 weight row.  9 (the validated default) shares the pixel stride and
-// makes every weight-fragment load of phase D 2-way bank conflicted (lane group g = 7 lands on the
-// banks of g = 0); 12 makes {12 g + tq} distinct mod 32 (opt-in TAPIR_B200_HEAD_W3S=12 until it
-// has run on a GPU; profiles/r01_ncu_summary.md).
+// W3S = 32-bit words per hid3 weight row.  With the pixel stride (9) every weight-fragment load
+// of phase D was 2-way bank conflicted (lane group g = 7 lands on the banks of g = 0: 49 M of the
+// 145 M shared wavefronts per launch, profiles/r01_ncu_summary.md); 12 makes {12 g + tq} distinct
+// mod 32.  Validated against the whole parity suite in round 2 (gpurun_out/head_w3s.log).
+constexpr int kW3Stride = 12;
 template <int W3S>
 struct HeadTcSmem {
   float cv[kTapW];
@@ -397,7 +398,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-static_assert(sizeof(HeadTcSmem<9>) <= 227 * 1024 && sizeof(HeadTcSmem<12>) <= 227 * 1024,
+static_assert(sizeof(HeadTcSmem<kW3Stride>) <= 227 * 1024,
               "head kernel shared memory exceeds the 227 KB opt-in limit");
 
 template <int W3S>
@@ -639,6 +640,214 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
   }  // map loop
 }
 
+
+// ------------------------------------------------------------------------ a6 head, any map size
+// initial_resolution != (256, 256) (constructor argument, tapir_model.py:86) gives a cost map that
+// is not 32 x 32.  Same arithmetic as the kernels above for a gh x gw map: one CTA per map,
+// ReLU(hid1) and the heat map staged in a per-CTA slice of the caller's workspace (L2 resident).
+// A correctness path (every published checkpoint / demo uses 256 x 256), not a tuned one.
+struct GenericRed {
+  float f[8 * 4];
+  int i[8];
+  float mean32[8][32];
+  float out[4];
+  int out_i;
+};
+
+__device__ __forceinline__ void generic_max_first(float v, int idx, GenericRed& r, float* ov, int* oi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float xv = __shfl_xor_sync(0xffffffffu, v, o);
+    const int xi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (xv > v || (xv == v && xi < idx)) { v = xv; idx = xi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { r.f[warp] = v; r.i[warp] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bv = r.f[0];
+    int bi = r.i[0];
+    for (int k = 1; k < 8; ++k)
+      if (r.f[k] > bv || (r.f[k] == bv && r.i[k] < bi)) { bv = r.f[k]; bi = r.i[k]; }
+    r.out[0] = bv;
+    r.out_i = bi;
+  }
+  __syncthreads();
+  *ov = r.out[0];
+  *oi = r.out_i;
+}
+
+__device__ __forceinline__ void generic_sum3(float a, float b, float c, GenericRed& r, float* oa,
+                                             float* ob, float* oc) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { r.f[warp * 4] = a; r.f[warp * 4 + 1] = b; r.f[warp * 4 + 2] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0, y = 0, z = 0;
+    for (int k = 0; k < 8; ++k) { x += r.f[k * 4]; y += r.f[k * 4 + 1]; z += r.f[k * 4 + 2]; }
+    r.out[0] = x; r.out[1] = y; r.out[2] = z;
+  }
+  __syncthreads();
+  *oa = r.out[0]; *ob = r.out[1]; *oc = r.out[2];
+}
+
+__global__ void __launch_bounds__(256) cost_volume_head_generic_kernel(
+    const tapir_head_weights w, const float* __restrict__ cost_volume, int T, int num_maps, int gh,
+    int gw, const float* __restrict__ query_tyx, float temperature, int init_h, int init_w,
+    float* __restrict__ scratch, float* __restrict__ points, float* __restrict__ occ_out,
+    float* __restrict__ expd_out, int* __restrict__ argmax_out) {
+  __shared__ GenericRed red;
+  __shared__ float w1s[16 * 9], b1s[16], w2s[16 * 9], w3s[32 * 16 * 9], b3s[32], w4s[16 * 32], b4s[16],
+      w5s[2 * 16], b5s[2];
+  const int tid = threadIdx.x;
+  const int pw = gw + 3, ph = gh + 3;  // index -1 .. size+1 (1 halo before, 2 after)
+  const int plane = pw * ph;
+  const int cells = gh * gw;
+  float* occ = scratch + (size_t)blockIdx.x * (16 * plane + cells);  // [16][ph][pw]
+  float* heat = occ + 16 * plane;                                    // [gh][gw]
+  for (int i = tid; i < 16 * 9; i += 256) { w1s[i] = w.hid1_w[i]; w2s[i] = w.hid2_w[i]; }
+  for (int i = tid; i < 32 * 16 * 9; i += 256) w3s[i] = w.hid3_w[i];
+  for (int i = tid; i < 512; i += 256) w4s[i] = w.hid4_w[i];
+  if (tid < 16) { b1s[tid] = w.hid1_b[tid]; b4s[tid] = w.hid4_b[tid]; }
+  if (tid < 32) { b3s[tid] = w.hid3_b[tid]; w5s[tid] = w.occ_w[tid]; }
+  if (tid < 2) b5s[tid] = w.occ_b[tid];
+  for (int i = tid; i < 16 * plane; i += 256) occ[i] = 0.f;  // halos stay zero for every map
+  const float b2 = w.hid2_b[0];
+  const int oh = (gh - 1) / 2 + 1, ow = (gw - 1) / 2 + 1;  // pad (0,2,0,2), 3x3, stride 2, no padding
+  for (int map = blockIdx.x; map < num_maps; map += gridDim.x) {
+    const int n = map / T, t = map - n * T;
+    const float* cv = cost_volume + (size_t)map * cells;
+    __syncthreads();
+    // hid1: conv3x3 1 -> 16, padding 1, ReLU
+    for (int i = tid; i < cells; i += 256) {
+      const int y = i / gw, x = i - y * gw;
+      float win[9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = y + ky - 1, xx = x + kx - 1;
+          win[ky * 3 + kx] = (yy >= 0 && yy < gh && xx >= 0 && xx < gw) ? cv[yy * gw + xx] : 0.f;
+        }
+      for (int co = 0; co < 16; ++co) {
+        float a = b1s[co];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a = fmaf(win[k], w1s[co * 9 + k], a);
+        occ[co * plane + (y + 1) * pw + (x + 1)] = fmaxf(a, 0.f);
+      }
+    }
+    __syncthreads();
+    // hid2: conv3x3 16 -> 1, padding 1, x temperature; running maximum
+    float lmax = -FLT_MAX;
+    for (int i = tid; i < cells; i += 256) {
+      const int y = i / gw, x = i - y * gw;
+      float a = b2;
+      for (int ci = 0; ci < 16; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            a = fmaf(occ[ci * plane + (y + ky) * pw + (x + kx)], w2s[ci * 9 + ky * 3 + kx], a);
+      const float h = a * temperature;
+      heat[i] = h;
+      lmax = fmaxf(lmax, h);
+    }
+    int dummy;
+    float gmax;
+    generic_max_first(lmax, 0, red, &gmax, &dummy);
+    float lsum = 0.f;
+    for (int i = tid; i < cells; i += 256) lsum += expf(heat[i] - gmax);
+    float gsum, u1, u2;
+    generic_sum3(lsum, 0.f, 0.f, red, &gsum, &u1, &u2);
+    float pbest = -1.f;
+    int ibest = 0;
+    for (int i = tid; i < cells; i += 256) {  // ascending i: the first maximum is kept
+      const float pr = expf(heat[i] - gmax) / gsum;
+      if (pr > pbest) { pbest = pr; ibest = i; }
+    }
+    float pm;
+    int am;
+    generic_max_first(pbest, ibest, red, &pm, &am);
+    const float cx = (float)(am % gw) + 0.5f, cy = (float)(am / gw) + 0.5f;
+    float sx = 0.f, sy = 0.f, sw = 0.f;
+    for (int i = tid; i < cells; i += 256) {
+      const int y = i / gw, x = i - y * gw;
+      const float px = (float)x + 0.5f, py = (float)y + 0.5f;
+      const float dx = px - cx, dy = py - cy;
+      if (dx * dx + dy * dy < 25.f) {
+        const float pr = expf(heat[i] - gmax) / gsum;
+        sx += px * pr; sy += py * pr; sw += pr;
+      }
+    }
+    float tx, ty, tw;
+    generic_sum3(sx, sy, sw, red, &tx, &ty, &tw);
+    // hid3: conv3x3 stride 2 16 -> 32 on the (0,2,0,2)-padded activation, ReLU, spatial mean
+    float msum[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) msum[c] = 0.f;
+    for (int o = tid; o < oh * ow; o += 256) {
+      const int oy = o / ow, ox = o - oy * ow;
+      float acc[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = b3s[c];
+      for (int ci = 0; ci < 16; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float v = occ[ci * plane + (2 * oy + ky + 1) * pw + (2 * ox + kx + 1)];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, w3s[(c * 16 + ci) * 9 + ky * 3 + kx], acc[c]);
+          }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) msum[c] += fmaxf(acc[c], 0.f);
+    }
+    {
+      const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float v = warp_sum(msum[c]);
+        if (lane == 0) red.mean32[warp][c] = v;
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {
+      float m = 0.f;
+      for (int k = 0; k < 8; ++k) m += red.mean32[k][tid];
+      red.mean32[0][tid] = m / (float)(oh * ow);
+    }
+    __syncthreads();
+    if (tid < 16) {
+      float a = b4s[tid];
+      for (int k = 0; k < 32; ++k) a = fmaf(red.mean32[0][k], w4s[tid * 32 + k], a);
+      red.mean32[1][tid] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    if (tid < 2) {
+      float a = b5s[tid];
+      for (int k = 0; k < 16; ++k) a = fmaf(red.mean32[1][k], w5s[tid * 16 + k], a);
+      const long long o = (long long)n * T + t;
+      if (tid == 0) occ_out[o] = a; else expd_out[o] = a;
+    }
+    if (tid == 0) {
+      const long long o = (long long)n * T + t;
+      const float den = fmaxf(tw, 1e-12f);
+      float px = __fdiv_rn(__fmul_rn(tx / den, (float)init_w), (float)gw);
+      float py = __fdiv_rn(__fmul_rn(ty / den, (float)init_h), (float)gh);
+      if (query_tyx != nullptr) {
+        const float qf = rintf(query_tyx[n * 3 + 0]);
+        if (qf == (float)t) { px = query_tyx[n * 3 + 2]; py = query_tyx[n * 3 + 1]; }
+      }
+      points[o * 2 + 0] = px;
+      points[o * 2 + 1] = py;
+      if (argmax_out != nullptr) argmax_out[o] = am;
+    }
+  }
+}
+
 }  // namespace
 
 int sample_query_features(const float* grid, int T, int gh, int gw, int C, const float* query_tyx,
@@ -656,18 +865,18 @@ int cost_volume_head(const tapir_head_weights* w, const float* cost_volume, int 
                      const float* query_tyx, float temperature, int init_h, int init_w,
                      float* points, float* occ, float* expd, int* argmax, cudaStream_t s) {
   static int use_simt = -1;
-  static int w3_stride = 9;
+  static PerDeviceOnce configured;
   if (use_simt < 0) {
     const char* e = getenv("TAPIR_B200_HEAD");
     use_simt = (e != nullptr && strcmp(e, "simt") == 0) ? 1 : 0;
+  }
+  if (configured.pending()) {
     TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(HeadSmem)));
-    TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(HeadTcSmem<9>)));
-    TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_tc_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(HeadTcSmem<12>)));
-    const char* ws = getenv("TAPIR_B200_HEAD_W3S");
-    w3_stride = (ws != nullptr && atoi(ws) == 12) ? 12 : 9;
+    TAPIR_CUDA(cudaFuncSetAttribute(cost_volume_head_tc_kernel<kW3Stride>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(HeadTcSmem<kW3Stride>)));
+    configured.mark();
   }
   TAPIR_CHECK_ARG(N <= 65535, "cost_volume_head: at most 65535 queries per call (got %d)", N);
   // head = 2,950,208 FLOP per (n,t); 4 KB map in, 16 B out
@@ -679,13 +888,8 @@ int cost_volume_head(const tapir_head_weights* w, const float* cost_volume, int 
   } else {
     const int maps = N * T;
     const int ctas = maps < num_sms() ? maps : num_sms();
-    if (w3_stride == 12) {
-      cost_volume_head_tc_kernel<12><<<ctas, kHT, sizeof(HeadTcSmem<12>), s>>>(
-          *w, cost_volume, T, maps, query_tyx, temperature, init_h, init_w, points, occ, expd, argmax);
-    } else {
-      cost_volume_head_tc_kernel<9><<<ctas, kHT, sizeof(HeadTcSmem<9>), s>>>(
-          *w, cost_volume, T, maps, query_tyx, temperature, init_h, init_w, points, occ, expd, argmax);
-    }
+    cost_volume_head_tc_kernel<kW3Stride><<<ctas, kHT, sizeof(HeadTcSmem<kW3Stride>), s>>>(
+        *w, cost_volume, T, maps, query_tyx, temperature, init_h, init_w, points, occ, expd, argmax);
   }
   count_launch();
   TAPIR_LAUNCH_CHECK("cost_volume_head_kernel");
@@ -698,13 +902,24 @@ struct CvPlan {
   __nv_bfloat16* q;
   __nv_bfloat16* g;
   float* cv;
-  int n_pad;
+  float* generic_scratch;  // maps other than 32 x 32 only
+  int generic_ctas;
 };
+constexpr int kGenericCtasPerSm = 4;
 size_t plan_cv(Arena& a, int N, int T, int gh, int gw, int C, CvPlan* p) {
   const long long cells = (long long)T * gh * gw;
   p->q = a.take<__nv_bfloat16>((size_t)N * C * kCvPlanes);
   p->g = a.take<__nv_bfloat16>((size_t)cells * C * kCvPlanes);
   p->cv = a.take<float>((size_t)N * cells);
+  p->generic_scratch = nullptr;
+  p->generic_ctas = 0;
+  if (gh != kG || gw != kG) {
+    const long long maps = (long long)N * T;
+    const long long cap = 148ll * kGenericCtasPerSm;  // independent of the device: sizes must agree
+    p->generic_ctas = (int)(maps < cap ? maps : cap);
+    p->generic_scratch =
+        a.take<float>((size_t)p->generic_ctas * (16 * (size_t)(gh + 3) * (gw + 3) + (size_t)gh * gw));
+  }
   return a.off;
 }
 }  // namespace
@@ -721,11 +936,7 @@ int cost_volume_tracks(const tapir_head_weights* w, const float* qfeat, const fl
                        void* ws, size_t ws_bytes, cudaStream_t s) {
   TAPIR_CHECK_ARG(w && qfeat && grid && points && occ && expd, "cost_volume_tracks: null pointer");
   TAPIR_CHECK_ARG(N > 0 && T > 0 && C % 64 == 0, "cost_volume_tracks: bad shape N=%d T=%d C=%d", N, T, C);
-  if (gh != kG || gw != kG) {
-    set_error("cost_volume_tracks: only a 32x32 cost-volume map (initial_resolution 256x256) is "
-              "implemented (got %dx%d)", gh, gw);
-    return kUnsupported;
-  }
+  TAPIR_CHECK_ARG(gh >= 2 && gw >= 2, "cost_volume_tracks: map %dx%d too small", gh, gw);
   Arena arena(ws, ws_bytes);
   CvPlan p;
   plan_cv(arena, N, T, gh, gw, C, &p);
@@ -746,6 +957,17 @@ int cost_volume_tracks(const tapir_head_weights* w, const float* qfeat, const fl
   g.out_f32 = p.cv; g.ldo = (int)cells;
   g.tag = "cost_volume.gemm";
   TAPIR_RETURN_IF(gemm(g, s));
+  if (gh != kG || gw != kG) {
+    // any other initial_resolution (tapir_model.py:86): generic-size head
+    ProfileScope ps("cost_volume.head", s, 2950208.0 / 1024.0 * gh * gw * N * T,
+                    (double)N * T * (4.0 * gh * gw + 16));
+    cost_volume_head_generic_kernel<<<p.generic_ctas, 256, 0, s>>>(
+        *w, p.cv, T, N * T, gh, gw, query_tyx, temperature, init_h, init_w, p.generic_scratch, points,
+        occ, expd, argmax);
+    count_launch();
+    TAPIR_LAUNCH_CHECK("cost_volume_head_generic_kernel");
+    return kOk;
+  }
   return cost_volume_head(w, p.cv, N, T, query_tyx, temperature, init_h, init_w, points, occ, expd,
                           argmax, s);
 }

@@ -13,13 +13,15 @@ from typing import Optional, Tuple
 
 import torch
 
+from tapnet_b200 import live
 from tapnet_b200 import tapir_model
 
 
 class OnlineTracker:
   """Graph-replayed per-frame step of a causal TAPIR model (`use_casual_conv=True`)."""
 
-  def __init__(self, model: 'tapir_model.TAPIR', height: int, width: int, num_points: int):
+  def __init__(self, model: 'tapir_model.TAPIR', height: int, width: int, num_points: int,
+               uint8_frames: bool = False):
     if not model.use_casual_conv:
       raise ValueError('OnlineTracker needs a causal model: TAPIR(use_casual_conv=True)')
     self.model = model
@@ -28,8 +30,13 @@ class OnlineTracker:
     self.dev = next(model.parameters()).device
     if self.dev.type != 'cuda':
       raise RuntimeError('OnlineTracker runs on CUDA only')
-    self._frame = torch.zeros(1, 1, height, width, 3, dtype=torch.float32, device=self.dev)
+    # uint8_frames: frames are raw [0, 255] camera frames (what pytorch_live_demo.py:139-141 holds
+    # before preprocess_frames); the normalisation runs inside the stem conv's loads
+    self._frame_dtype = torch.uint8 if uint8_frames else torch.float32
+    self._frame = torch.zeros(1, 1, height, width, 3, dtype=self._frame_dtype, device=self.dev)
     self._graph: Optional[torch.cuda.CUDAGraph] = None
+    self._graph_sig = None
+    self._pinned = False
     self.query_features = None
     self.state = None
     self._out = None
@@ -55,7 +62,7 @@ class OnlineTracker:
     return self.query_features
 
   def _as_frame(self, frame):
-    frame = frame.to(self.dev, torch.float32)
+    frame = frame.to(self.dev, self._frame_dtype, non_blocking=True)
     if frame.dim() == 3:
       frame = frame[None, None]
     if tuple(frame.shape[2:4]) != self.hw:
@@ -64,15 +71,13 @@ class OnlineTracker:
 
   def _step_eager(self):
     grids = self.model.get_feature_grids(self._frame, False)
+    # single-frame step: the causal state is updated in place (causal_context_out = state)
     r = self.model.estimate_trajectories(self.hw, False, grids, self.query_features, None, 64,
-                                         causal_context=self.state, get_causal_context=True)
+                                         causal_context=self.state, get_causal_context=True,
+                                         causal_context_out=self.state)
     tracks = r['tracks'][-1]
     occ, expd = r['occlusion'][-1], r['expected_dist'][-1]
-    # pytorch_live_demo.py:57-59 postprocess_occlusions
-    visibles = (1 - torch.sigmoid(occ)) * (1 - torch.sigmoid(expd)) > 0.5
-    for new, old in zip(r['causal_context'], self.state):
-      for k in old:
-        old[k].copy_(new[k])
+    visibles = live.postprocess_occlusions(occ, expd)  # pytorch_live_demo.py:57-59
     return tracks, visibles, occ, expd
 
   def _capture(self):
@@ -95,6 +100,32 @@ class OnlineTracker:
       for k in d:
         d[k].copy_(sv[k])
     self._graph = g
+    # The graph holds RAW pointers into the model's workspaces and packed weight planes.  Pin
+    # the workspaces (TAPIR._workspace then parks outgrown buffers instead of freeing them) and
+    # remember which buffers / weights the capture saw: step() re-captures when another caller
+    # of the same model (a larger offline clip, a second tracker, load_state_dict) replaced them.
+    if not self._pinned:
+      self.model._ws_pins += 1
+      self._pinned = True
+    self._graph_sig = self._model_sig()
+
+  def _model_sig(self):
+    return (self.model._ws_generation, self.model._param_sig())
+
+  def close(self):
+    """Drops the graph and releases the workspace pin."""
+    self._graph = None
+    if self._pinned:
+      self.model._ws_pins -= 1
+      self._pinned = False
+      if self.model._ws_pins == 0:
+        self.model._ws_retired.clear()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
 
   # -- pytorch_live_demo.py:62-85 online_model_predict
   def step(self, frame: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -103,6 +134,8 @@ class OnlineTracker:
     if self.query_features is None:
       raise RuntimeError('call init(frame, query_points) first')
     self._frame.copy_(self._as_frame(frame))
+    if self._graph is not None and self._graph_sig != self._model_sig():
+      self._graph = None  # stale pointers: the model's buffers or weights changed since capture
     if self._graph is None:
       self._capture()
     self._graph.replay()

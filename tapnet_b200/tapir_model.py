@@ -80,6 +80,24 @@ def _ptr(t):
   return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _on_model_device(fn):
+  """Runs a TAPIR method with the model's CUDA device current.  Kernels launch on the current
+  device and the C library keeps per-device state (shared-memory attributes, error flag), so
+  `build_model(device='cuda:1')` must work without the caller calling torch.cuda.set_device
+  (the reference runs on whatever device its tensors live on)."""
+  import functools  # pylint: disable=g-import-not-at-top
+
+  @functools.wraps(fn)
+  def wrapper(self, *args, **kwargs):
+    dev = next(self.parameters()).device
+    if dev.type != 'cuda':
+      # argument errors are reported in the reference's order; _device_check then raises
+      return fn(self, *args, **kwargs)
+    with torch.cuda.device(dev):
+      return fn(self, *args, **kwargs)
+  return wrapper
+
+
 class TAPIR(nn.Module):
   """TAPIR model (B200 engine).  See the module docstring.
 
@@ -136,7 +154,14 @@ class TAPIR(nn.Module):
     self._packed = None
     self._packed_sig = None
     self._ws = {}
+    self._ws_retired = []
+    self._ws_pins = 0
+    self._ws_generation = 0
     self._consts = {}
+    # tests / diagnostics: when True, estimate_trajectories keeps the stage-A arg-max cell of
+    # every (query, frame) heat map in `last_stage_a_argmax` ([B, N, T] int32)
+    self.capture_stage_a_argmax = False
+    self.last_stage_a_argmax = None
 
   # ------------------------------------------------------------------ parameter plumbing
   def _register(self, key, tensor):
@@ -174,8 +199,10 @@ class TAPIR(nn.Module):
         raise RuntimeError(f'tensor on {t.device}, model on {dev}')
     return dev
 
-  def _stream(self):
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+  def _stream(self, dev=None):
+    # the current stream OF THE MODEL'S DEVICE (every public method runs its launches inside
+    # `torch.cuda.device(dev)`, so the C side's per-device caches and the pointers agree)
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
   def _const(self, values, dev):
     """Small constant vectors, cached: creating them per call costs a blocking H2D copy."""
@@ -187,13 +214,21 @@ class TAPIR(nn.Module):
     return t
 
   def _workspace(self, name, nbytes, dev):
+    """Grow-only scratch.  A buffer that is outgrown is parked in `_ws_retired` instead of
+    being freed while `_ws_pins` > 0: a captured CUDA graph (streaming.OnlineTracker) holds raw
+    pointers into it.  `_ws_generation` changes whenever a buffer is replaced, so graph owners
+    can tell that their capture no longer describes the model's current buffers."""
     ws = self._ws.get(name)
     if ws is None or ws.numel() < nbytes or ws.device != dev:
+      if ws is not None and self._ws_pins > 0:
+        self._ws_retired.append(ws)
       ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
       self._ws[name] = ws
+      self._ws_generation += 1
     return ws
 
   # ------------------------------------------------------------------ weight packing
+  @_on_model_device
   def _pack(self):
     sig = self._param_sig()
     if self._packed is not None and self._packed_sig == sig:
@@ -203,7 +238,7 @@ class TAPIR(nn.Module):
     dev = next(self.parameters()).device
     P = self._planes
     keep = []  # tensors referenced by raw pointers below
-    stream = self._stream()
+    stream = self._stream(dev)
 
     def f32(t):
       t = t.to(device=dev, dtype=torch.float32).contiguous().clone()
@@ -322,6 +357,7 @@ class TAPIR(nn.Module):
         unrefined_expected_dist=trajectories['expected_dist'][:-1],
     )
 
+  @_on_model_device
   def get_feature_grids(
       self,
       video: torch.Tensor,
@@ -351,7 +387,7 @@ class TAPIR(nn.Module):
     curr_resolution = (-1, -1)
     latent = hires = None
     shape_hw = None
-    stream = self._stream()
+    stream = self._stream(dev)
     for resolution in all_required:
       if resolution[0] % 8 != 0 or resolution[1] % 8 != 0:
         raise ValueError('Image resolution must be a multiple of 8.')
@@ -403,6 +439,7 @@ class TAPIR(nn.Module):
       resize_im_shape.append(torch.Size(shape_hw))
     return FeatureGrids(tuple(feature_grid), tuple(hires_feats), tuple(resize_im_shape))
 
+  @_on_model_device
   def get_query_features(
       self,
       video: torch.Tensor,
@@ -416,7 +453,7 @@ class TAPIR(nn.Module):
       feature_grids = self.get_feature_grids(video, is_training, refinement_resolutions)
     dev = self._device_check(query_points)
     lib = _lib.load()
-    stream = self._stream()
+    stream = self._stream(dev)
     shape = video.shape
     qp = query_points.to(torch.float32).contiguous()
     b, nq, _ = qp.shape
@@ -431,7 +468,7 @@ class TAPIR(nn.Module):
           grid = grid.contiguous()
           _, t, gh, gw, c = grid.shape
           out = torch.empty(b, nq, c, dtype=torch.float32, device=dev)
-          for bi in range(b):
+          for bi in range(b if nq > 0 else 0):
             _lib.check(lib.tapir_sample_query_features(
                 _ptr(grid[bi]), t, gh, gw, c, _ptr(qp[bi]), nq, int(shape[1]), int(shape[2]),
                 int(shape[3]), _ptr(out[bi]), stream), 'tapir_sample_query_features')
@@ -442,6 +479,7 @@ class TAPIR(nn.Module):
     return QueryFeatures(tuple(query_feats), tuple(hires_query_feats),
                          tuple(feature_grids.resolutions))
 
+  @_on_model_device
   def estimate_trajectories(
       self,
       video_size: Tuple[int, int],
@@ -452,8 +490,14 @@ class TAPIR(nn.Module):
       query_chunk_size: Optional[int] = None,
       causal_context: Optional[list] = None,
       get_causal_context: bool = False,
+      causal_context_out: Optional[list] = None,
   ) -> Mapping[str, Any]:
     """Reference tapir_model.py:394-578.
+
+    `causal_context_out` (extension, optional): list of dicts of preallocated [B, N, 2, 512|2048]
+    tensors that receive the new causal context instead of fresh allocations.  For single-frame
+    steps (T == 1, the streaming case) it may be `causal_context` itself: the state is then
+    updated in place, which saves a 1 GB copy per frame at 1024 points.
 
     `query_chunk_size` only bounds memory in the reference (queries are independent,
     SURVEY.md 2.2); here chunks are sized by rows (queries x frames) to keep all 148 SMs busy
@@ -464,7 +508,7 @@ class TAPIR(nn.Module):
     dev = self._device_check(query_features.lowres[0])
     lib = _lib.load()
     pk = self._pack()
-    stream = self._stream()
+    stream = self._stream(dev)
     P = self._planes
     ih, iw = self.initial_resolution
     vh, vw = int(video_size[0]), int(video_size[1])
@@ -482,13 +526,50 @@ class TAPIR(nn.Module):
     occ_out = [new(B, N, T) for _ in range(num_iters + 1)]
     expd_out = [new(B, N, T) for _ in range(num_iters + 1)]
     trk_out = [new(B, N, T, 2) for _ in range(num_iters + 1)]
-    new_ctx = None
-    if get_causal_context:
-      new_ctx = [{} for _ in range(num_iters)]
-      for d in new_ctx:
+    # Causal context bookkeeping follows nets.py:143-176: a block only produces a new context
+    # when it was GIVEN one (new_causal_context is filled inside `if causal_context is not None`),
+    # so get_causal_context without causal_context yields empty dicts, exactly like the reference.
+    if causal_context is not None:
+      if not self.use_casual_conv:
+        raise ValueError('causal_context needs a causal model (use_casual_conv=True); the '
+                         'reference would run its non-causal convolutions over the context rows')
+      if len(causal_context) < num_iters:
+        raise ValueError(f'causal_context has {len(causal_context)} entries, {num_iters} needed')
+      for d in causal_context[:num_iters]:
         for i in range(nb):
-          d[f'block_{i}_causal_1'] = new(B, N, 2, 512)
-          d[f'block_{i}_causal_2'] = new(B, N, 2, 2048)
+          for key, width in ((f'block_{i}_causal_1', 512), (f'block_{i}_causal_2', 2048)):
+            if tuple(d[key].shape) != (B, N, 2, width):
+              raise ValueError(f'causal_context[{key}] has shape {tuple(d[key].shape)}, expected '
+                               f'{(B, N, 2, width)}')
+    new_ctx = None
+    if get_causal_context and causal_context is not None and causal_context_out is not None:
+      if T != 1 and any(causal_context_out[it][k].data_ptr() == causal_context[it][k].data_ptr()
+                        for it in range(num_iters) for k in causal_context[it]):
+        raise ValueError('causal_context_out may alias causal_context only for single-frame steps')
+      new_ctx = [dict(d) for d in causal_context_out[:num_iters]]
+      for d in new_ctx:
+        for k, v in d.items():
+          if not (v.is_contiguous() and v.dtype == torch.float32 and v.device == dev):
+            raise ValueError(f'causal_context_out[{k}] must be a contiguous fp32 tensor on {dev}')
+    elif get_causal_context:
+      new_ctx = [{} for _ in range(num_iters)]
+      if causal_context is not None:
+        for d in new_ctx:
+          for i in range(nb):
+            d[f'block_{i}_causal_1'] = new(B, N, 2, 512)
+            d[f'block_{i}_causal_2'] = new(B, N, 2, 2048)
+    write_ctx = get_causal_context and causal_context is not None
+    am_out = None
+    if self.capture_stage_a_argmax:
+      am_out = torch.empty(B, N, T, dtype=torch.int32, device=dev)
+      self.last_stage_a_argmax = am_out
+    if N == 0 or T == 0:
+      # nothing to track (the reference fails in torch.cat on an empty chunk list,
+      # tapir_model.py:556-559; returning correctly shaped empty tensors is the useful behaviour)
+      out = dict(occlusion=occ_out, tracks=trk_out, expected_dist=expd_out)
+      if get_causal_context:
+        out['causal_context'] = new_ctx
+      return out
 
     # pooled pyramid level: once per resolution level (the reference recomputes it every
     # iteration of every chunk, tapir_model.py:519-527)
@@ -527,7 +608,8 @@ class TAPIR(nn.Module):
         ws = self._workspace('cost_volume', nbytes, dev)
         _lib.check(lib.tapir_cost_volume_tracks(
             ctypes.byref(pk['head']), _ptr(qf0), _ptr(grid0), n, T, gh0, gw0, c0, _ptr(qp),
-            float(self.softmax_temperature), ih, iw, _ptr(pos), _ptr(occ0), _ptr(expd0), None,
+            float(self.softmax_temperature), ih, iw, _ptr(pos), _ptr(occ0), _ptr(expd0),
+            _ptr(am_out[bi, sl]) if am_out is not None else None,
             _ptr(ws), ws.numel(), stream), 'tapir_cost_volume_tracks')
         # train2orig (tapir_model.py:435-441)
         torch.div(pos * self._const([vw, vh], dev), self._const([iw, ih], dev),
@@ -588,7 +670,7 @@ class TAPIR(nn.Module):
             io.ctx1_in = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in c1])
             io.ctx2_in = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in c2])
           o1 = o2 = None
-          if get_causal_context:
+          if write_ctx:
             o1 = [new_ctx[it][f'block_{i}_causal_1'][bi, sl] for i in range(nb)]
             o2 = [new_ctx[it][f'block_{i}_causal_2'][bi, sl] for i in range(nb)]
             io.ctx1_out = (ctypes.c_void_p * nb)(*[t.data_ptr() for t in o1])
@@ -673,6 +755,20 @@ def build_model(checkpoint_path: Optional[str] = None, device: str = 'cuda', **t
   """BASELINE.json north_star names a `build_model`; the reference spells it out at each call
   site as TAPIR(...) + load_state_dict(torch.load(path)) + .to(device).eval()
   (tapnet/pytorch_live_demo.py:110-117).  This is that sequence."""
+  if checkpoint_path is not None and str(checkpoint_path).endswith('.npy'):
+    # Haiku parameter tree (the format "Online TAPIR" is published in, README.md:165, and what
+    # robotap/tapir_clustering.py:track_many_points is handed): convert, then the usual sequence
+    from tapnet_b200 import convert  # pylint: disable=g-import-not-at-top
+    import numpy as _np  # pylint: disable=g-import-not-at-top
+    ckpt = _np.load(checkpoint_path, allow_pickle=True).item()
+    params = ckpt['params'] if 'params' in ckpt else ckpt
+    kwargs = convert.infer_model_kwargs(params)  # pyramid_level / extra_convs from the tree
+    kwargs.update(tapir_kwargs)
+    state_dict = convert.convert_haiku_params(params, kwargs['pyramid_level'],
+                                              kwargs['extra_convs'])
+    model = TAPIR(**kwargs)
+    model.load_state_dict(state_dict)
+    return model.to(device).eval()
   model = TAPIR(**tapir_kwargs)
   if checkpoint_path is not None:
     model.load_state_dict(torch.load(checkpoint_path, map_location='cpu'))

@@ -1,7 +1,8 @@
 """End-to-end parity: CUDA path vs the reference's golden outputs and vs the CPU oracle.
 
-Tolerances are BASELINE.json's: tracks 1e-3 px, occlusion / expected_dist logits 1e-4
-(arg-max indices are checked bit-exact in test_stages_gpu.py::test_cost_volume_tracks).
+Tolerances are BASELINE.json's: tracks 1e-3 px, occlusion / expected_dist logits 1e-4, stage-A
+arg-max cell indices bit-exact against the indices the reference itself computed on the same
+clip (`stage_a_argmax` in every golden file, recorded by oracle/make_golden.py).
 """
 import numpy as np
 import pytest
@@ -20,6 +21,16 @@ TRACK_TOL = 1e-3
 LOGIT_TOL = 1e-4
 
 
+def _argmax_check(name, model, g):
+  """Stage-A arg-max cells of the last estimate_trajectories call vs the reference's own."""
+  got = model.last_stage_a_argmax[0].cpu().numpy()
+  want = g['stage_a_argmax']
+  mism = int((got != want).sum())
+  U.record(f'argmax_{name}', maps=int(want.size), mismatches=mism,
+           min_top2_margin=float(g['stage_a_margin'].min()))
+  assert mism == 0, f'{mism}/{want.size} stage-A arg-max cells differ from the reference'
+
+
 def _inputs(meta):
   video = synth.make_video(meta['T'], meta['H'], meta['W'], seed=meta['video_seed'])
   q = synth.make_queries(meta['N'], meta['T'], meta['H'], meta['W'], seed=meta['query_seed'],
@@ -36,8 +47,11 @@ def test_forward_matches_reference_golden(name):
   model, _, _ = get_model(kw.get('pyramid_level', 1), kw.get('extra_convs', True),
                           kw.get('use_casual_conv', False))
   video, q = _inputs(meta)
+  model.capture_stage_a_argmax = True
   out = model(video.cuda(), q.cuda())
   torch.cuda.synchronize()
+  model.capture_stage_a_argmax = False
+  _argmax_check(name, model, g)
   e_t = np.abs(out['tracks'][0].cpu().numpy() - g['tracks']).max()
   e_o = np.abs(out['occlusion'][0].cpu().numpy() - g['occlusion']).max()
   e_e = np.abs(out['expected_dist'][0].cpu().numpy() - g['expected_dist']).max()
@@ -75,10 +89,7 @@ def test_streaming_matches_reference_golden():
   assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_e < LOGIT_TOL and e_s < 5e-4
 
 
-@pytest.mark.skipif(__import__('os').environ.get('TAPIR_B200_EXPERIMENTAL') != '1',
-                    reason='added after the round-1 GPU budget ended: run once with '
-                           'TAPIR_B200_EXPERIMENTAL=1 (scripts/gpu_ci.sh experimental), then enable')
-def test_live_demo_shape_480_two_levels_experimental():
+def test_live_demo_shape_480_two_levels():
   """The README's live-demo shape (480x480, 8 points, refinement levels 256 + 480 = 8 iterations):
   offline-causal forward and per-frame streaming against the reference's golden outputs."""
   g = load_golden('causal_480x3_n8')
@@ -86,7 +97,10 @@ def test_live_demo_shape_480_two_levels_experimental():
   model, _, _ = get_model(causal=True)
   video, q = _inputs(meta)
   video, q = video.cuda(), q.cuda()
+  model.capture_stage_a_argmax = True
   out = model(video, q)
+  model.capture_stage_a_argmax = False
+  _argmax_check('causal_480x3_n8', model, g)
   e_t = np.abs(out['tracks'][0].cpu().numpy() - g['tracks']).max()
   e_o = np.abs(out['occlusion'][0].cpu().numpy() - g['occlusion']).max()
   e_e = np.abs(out['expected_dist'][0].cpu().numpy() - g['expected_dist']).max()
@@ -112,16 +126,17 @@ def test_live_demo_shape_480_two_levels_experimental():
   assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_s < 5e-4
 
 
-@pytest.mark.skipif(__import__('os').environ.get('TAPIR_B200_EXPERIMENTAL') != '1',
-                    reason='added after the round-1 GPU budget ended (scripts/gpu_ci.sh experimental)')
-def test_forward_1024_three_levels_golden_experimental():
+def test_forward_1024_three_levels_golden():
   """BASELINE config 5's pyramid (256 / 512 / 1024, 12 iterations) against the reference's golden
   outputs (the enabled c5 test compares with the oracle on a reduced clip)."""
   g = load_golden('bootstapir_1024x2_n6')
   meta = g['meta']
   model, _, _ = get_model()
   video, q = _inputs(meta)
+  model.capture_stage_a_argmax = True
   out = model(video.cuda(), q.cuda())
+  model.capture_stage_a_argmax = False
+  _argmax_check('bootstapir_1024x2_n6', model, g)
   assert len(out['unrefined_tracks']) == 12
   e_t = np.abs(out['tracks'][0].cpu().numpy() - g['tracks']).max()
   e_o = np.abs(out['occlusion'][0].cpu().numpy() - g['occlusion']).max()
@@ -129,6 +144,27 @@ def test_forward_1024_three_levels_golden_experimental():
   U.record('e2e_1024_three_levels', tracks_err=e_t, occ_err=e_o, expd_err=e_e)
   # tracks are in 1024-pixel units here: the 1e-3 px budget is stated at 256^2
   assert e_t < 4 * TRACK_TOL and e_o < LOGIT_TOL and e_e < LOGIT_TOL
+
+
+def test_initial_resolution_other_than_256_golden():
+  """TAPIR(initial_resolution=(192, 320)) (ctor argument, tapir_model.py:86): 24 x 40 cost map,
+  generic-size head; against the reference's golden outputs incl. its arg-max cells."""
+  name = 'bootstapir_ir192x320x3_n10'
+  g = load_golden(name)
+  meta = g['meta']
+  sd = synth.make_state_dict(0)
+  model = tapir_model.TAPIR(pyramid_level=1, initial_resolution=tuple(meta['model_kwargs']['initial_resolution']))
+  model.load_state_dict(sd)
+  model = model.cuda().eval()
+  video, q = _inputs(meta)
+  model.capture_stage_a_argmax = True
+  out = model(video.cuda(), q.cuda())
+  _argmax_check(name, model, g)
+  e_t = np.abs(out['tracks'][0].cpu().numpy() - g['tracks']).max()
+  e_o = np.abs(out['occlusion'][0].cpu().numpy() - g['occlusion']).max()
+  e_e = np.abs(out['expected_dist'][0].cpu().numpy() - g['expected_dist']).max()
+  U.record(f'e2e_{name}', tracks_err=e_t, occ_err=e_o, expd_err=e_e)
+  assert e_t < TRACK_TOL and e_o < LOGIT_TOL and e_e < LOGIT_TOL
 
 
 def test_chunking_and_oracle_agreement_larger():

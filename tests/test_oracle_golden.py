@@ -16,7 +16,8 @@ TRACK_TOL = 5e-4
 LOGIT_TOL = 5e-5
 
 OFFLINE = ['c1_bootstapir_256x8_n16', 'tapir_pl0_noextra_256x4_n8', 'bootstapir_320x384x4_n12',
-           'causal_256x6_n16', 'causal_480x3_n8', 'bootstapir_1024x2_n6']
+           'causal_256x6_n16', 'causal_480x3_n8', 'bootstapir_1024x2_n6',
+           'bootstapir_ir192x320x3_n10']
 CAUSAL = ['causal_256x6_n16', 'causal_480x3_n8']   # the second: live-demo shape, two levels
 
 
@@ -24,7 +25,8 @@ def _setup(g):
   m = g['meta']
   kw = m['model_kwargs']
   cfg = O.Config(pyramid_level=kw.get('pyramid_level', 1), extra_convs=kw.get('extra_convs', True),
-                 use_casual_conv=kw.get('use_casual_conv', False))
+                 use_casual_conv=kw.get('use_casual_conv', False),
+                 initial_resolution=tuple(kw.get('initial_resolution', (256, 256))))
   sd = synth.make_state_dict(m['weights_seed'], cfg.pyramid_level, cfg.extra_convs)
   video = synth.make_video(m['T'], m['H'], m['W'], seed=m['video_seed'])
   q = synth.make_queries(m['N'], m['T'], m['H'], m['W'], seed=m['query_seed'],
@@ -47,6 +49,13 @@ def test_oracle_matches_reference_golden(name):
     np.testing.assert_allclose(qf.lowres[-1][0, :, ::8].numpy(), g['qfeat_lowres'], atol=2e-5)
     np.testing.assert_allclose(qf.hires[-1][0, :, ::8].numpy(), g['qfeat_hires'], atol=2e-5)
     tr = O.estimate_trajectories(sd, cfg, video.shape[-3:-1], grids, qf, q, 64)
+    # stage-A arg-max cells: the oracle must pick the reference's cell on every heat map
+    h0, w0 = grids.lowres[0].shape[2:4]
+    scale = torch.tensor([1.0, cfg.initial_resolution[0] / video.shape[2],
+                          cfg.initial_resolution[1] / video.shape[3]])
+    _, _, _, am, _ = O.tracks_from_cost_volume(sd, cfg, qf.lowres[0], grids.lowres[0], q * scale,
+                                               return_debug=True)
+    assert np.array_equal(am[0].numpy().astype(np.int32), g['stage_a_argmax']), name
   for i in range(len(tr['tracks'])):
     np.testing.assert_allclose(tr['tracks'][i][0].numpy(), g['tracks_iters'][i], atol=TRACK_TOL)
     np.testing.assert_allclose(tr['occlusion'][i][0].numpy(), g['occlusion_iters'][i],

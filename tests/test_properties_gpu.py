@@ -132,3 +132,108 @@ def test_c4_sharded_equals_single_gpu():
   p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
   print(p.stdout[-2000:], p.stderr[-2000:])
   assert p.returncode == 0 and 'MULTI_GPU_OK' in p.stdout
+
+
+def test_update_query_features_and_tracker_update_query_on_device():
+  """`TAPIR.update_query_features` (reference tapir_model.py:774-806) on CUDA tensors and its
+  graph-safe twin `OnlineTracker.update_query` (pytorch_live_demo.py:188-200): re-targeting a
+  point overwrites exactly that point's query features, zeroes exactly its causal state (through
+  every aliased dict), and the following frames equal a tracker that started from scratch with
+  the new point at that slot and a zero state for it."""
+  from tapnet_b200 import streaming
+  model, sd, cfg = get_model(causal=True)
+  T, N, idx = 4, 16, 5
+  video = synth.make_video(T).cuda()
+  q = synth.make_queries(N, T, frame0_only=True).cuda()
+  # --- the model method itself, CUDA tensors, against the oracle-free definition
+  g0 = model.get_feature_grids(video[:, :1], False)
+  qf = model.get_query_features(video[:, :1], False, q, g0)
+  qf = tapir_model.QueryFeatures(tuple(t.clone() for t in qf.lowres),
+                                 tuple(t.clone() for t in qf.hires), qf.resolutions)
+  before_lo = [t.clone() for t in qf.lowres]
+  state = model.construct_initial_causal_state(N, len(qf.resolutions) - 1)
+  state = [{k: torch.full_like(v, 3.0).cuda() for k, v in d.items()} for d in state]
+  new_pt = torch.tensor([[[0.0, 77.25, 130.5]]], device='cuda')
+  g1 = model.get_feature_grids(video[:, 1:2], False)
+  new_qf = model.get_query_features(video[:, 1:2], False, new_pt, g1)
+  qf2, state2 = model.update_query_features(qf, new_qf, idx, state)
+  for lvl in range(len(qf2.lowres)):
+    assert torch.equal(qf2.lowres[lvl][:, idx], new_qf.lowres[lvl][:, 0])
+    assert torch.equal(qf2.hires[lvl][:, idx], new_qf.hires[lvl][:, 0])
+    keep = [i for i in range(N) if i != idx]
+    assert torch.equal(qf2.lowres[lvl][:, keep], before_lo[lvl][:, keep])
+  for d in state2:
+    for k, v in d.items():
+      assert float(v[:, idx].abs().max()) == 0.0, k
+      assert float((v[:, [i for i in range(N) if i != idx]] - 3.0).abs().max()) == 0.0, k
+  # --- tracker: re-target after 2 frames, compare frames 2.. with explicit eager calls
+  trk = streaming.OnlineTracker(model, 256, 256, N)
+  trk.init(video[0, 0], q)
+  trk.step(video[0, 0])
+  trk.step(video[0, 1])
+  trk.update_query(video[0, 1], new_pt[0, 0], idx)
+  # eager twin: same features / state, advanced by the model's own methods
+  qf_e = tapir_model.QueryFeatures(tuple(t.clone() for t in trk.query_features.lowres),
+                                   tuple(t.clone() for t in trk.query_features.hires),
+                                   trk.query_features.resolutions)
+  st_e = [{k: v.clone() for k, v in d.items()} for d in trk.state]
+  assert float(st_e[0]['block_0_causal_1'][:, idx].abs().max()) == 0.0
+  assert torch.equal(qf_e.lowres[-1][:, idx], new_qf.lowres[-1][:, 0])
+  for t in (2, 3):
+    tracks, _ = trk.step(video[0, t])
+    gr = model.get_feature_grids(video[:, t:t + 1], False)
+    r = model.estimate_trajectories((256, 256), False, gr, qf_e, None, 64, causal_context=st_e,
+                                    get_causal_context=True)
+    st_e = r['causal_context']
+    assert torch.equal(tracks, r['tracks'][-1]), f'frame {t}'
+  trk.close()
+  U.record('update_query_gpu', ok=1)
+
+
+def test_zero_queries_and_context_semantics():
+  """Edge cases of the reference surface: no query points (empty, correctly shaped outputs), and
+  get_causal_context without a causal_context (empty dicts, nets.py:143-176)."""
+  model, _, _ = get_model()
+  T = 3
+  video = synth.make_video(T).cuda()
+  q0 = torch.zeros(1, 0, 3, device='cuda')
+  out = model(video, q0)
+  assert tuple(out['tracks'].shape) == (1, 0, T, 2)
+  assert tuple(out['occlusion'].shape) == (1, 0, T)
+  assert len(out['unrefined_tracks']) == 4
+  q = synth.make_queries(4, T).cuda()
+  g = model.get_feature_grids(video, False)
+  qf = model.get_query_features(video, False, q, g)
+  r = model.estimate_trajectories((256, 256), False, g, qf, q, 64, get_causal_context=True)
+  assert len(r['causal_context']) == 4 and all(d == {} for d in r['causal_context'])
+  with pytest.raises(ValueError):
+    st = [{k: v.cuda() for k, v in d.items()} for d in model.construct_initial_causal_state(4, 1)]
+    model.estimate_trajectories((256, 256), False, g, qf, q, 64, causal_context=st)
+
+
+def test_tracker_survives_workspace_growth():
+  """A captured graph bakes raw workspace pointers; a later, larger call on the same model
+  replaces the model's workspaces.  The tracker must notice and stay correct."""
+  from tapnet_b200 import streaming
+  model, _, _ = get_model(causal=True)
+  T, N = 4, 32
+  video = synth.make_video(T).cuda()
+  q = synth.make_queries(N, T, frame0_only=True).cuda()
+
+  def run(disturb):
+    trk = streaming.OnlineTracker(model, 256, 256, N)
+    trk.init(video[0, 0], q)
+    outs = []
+    for t in range(T):
+      if disturb and t == 2:
+        gen = model._ws_generation
+        big = synth.make_queries(8192, T).cuda()  # outgrows every workspace of the tracker
+        model(video, big)
+        assert model._ws_generation != gen and model._ws_retired, 'workspaces were not replaced'
+      outs.append(trk.step(video[0, t])[0].clone())
+    trk.close()
+    return torch.cat(outs, 2)
+
+  a, b = run(False), run(True)
+  assert torch.equal(a, b)
+  U.record('tracker_workspace_growth', equal=1)

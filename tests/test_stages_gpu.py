@@ -128,7 +128,11 @@ def test_cost_volume_tracks():
   assert e_p < 1e-3 and e_o < 1e-4 and e_e < 1e-4
 
 
-@pytest.mark.parametrize('cfg_case', [(1, 32, 32, True), (1, 40, 48, True), (0, 32, 32, False)])
+# (pyramid_level, gh, gw, use_last).  24 x 72 is a 3:1 panoramic grid: the reference spaces the x
+# samples gw/gh = 3 cells apart (x is normalised by h, utils.py:104), wider than the 16-column
+# cell box, so the kernel's per-sample path is exercised (levels 0/1) next to the box path.
+@pytest.mark.parametrize('cfg_case', [(1, 32, 32, True), (1, 40, 48, True), (0, 32, 32, False),
+                                      (1, 24, 72, True)])
 def test_local_corr(cfg_case):
   pyr, gh, gw, use_last = cfg_case
   model, sd, cfg = get_model(pyramid_level=pyr, extra_convs=(pyr == 1))
@@ -197,6 +201,44 @@ def test_local_corr(cfg_case):
   U.record(f'local_corr_pyr{pyr}_{gh}x{gw}_last{int(use_last)}', corr_err=e_corr, feat_err=e_feat,
            head_err=e_head, corr_scale=ref.abs().max().item())
   assert e_corr < 2e-5 * max(1.0, ref.abs().max().item()) and e_feat < 1e-6 and e_head < 1e-6
+
+
+@pytest.mark.parametrize('shape', [(24, 40), (48, 16)])
+def test_cost_volume_tracks_any_map_size(shape):
+  """initial_resolution != (256, 256) (ctor argument, tapir_model.py:86): the cost map is not
+  32 x 32 and the generic-size head runs.  Same checks as the 32 x 32 case."""
+  gh, gw = shape
+  model, sd, cfg = get_model()
+  lib = _lib.load()
+  pk = model._pack()
+  T, N = 3, 20
+  grid = _unit_grid(T, gh, gw, 256, 15)
+  g = torch.Generator().manual_seed(16)
+  idx = torch.randint(0, T * gh * gw, (N,), generator=g)
+  qf = grid.reshape(-1, 256)[idx] + 0.05 * torch.randn(N, 256, generator=g)
+  qf = (qf / qf.norm(dim=-1, keepdim=True))[None]
+  ih, iw = gh * 8, gw * 8
+  qp = synth.make_queries(N, T, ih, iw)
+  cfg2 = cfg._replace(initial_resolution=(ih, iw))
+  with torch.no_grad():
+    pts, occ, expd, am, _ = O.tracks_from_cost_volume(sd, cfg2, qf, grid, qp, return_debug=True)
+  dev = 'cuda'
+  o_pts = torch.empty(N, T, 2, device=dev)
+  o_occ = torch.empty(N, T, device=dev)
+  o_exp = torch.empty(N, T, device=dev)
+  o_am = torch.empty(N, T, dtype=torch.int32, device=dev)
+  nbytes = lib.tapir_cost_volume_workspace_bytes(N, T, gh, gw, 256)
+  ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+  qf_d, grid_d, qp_d = qf[0].cuda().contiguous(), grid[0].cuda().contiguous(), qp[0].cuda().contiguous()
+  _lib.check(lib.tapir_cost_volume_tracks(
+      ctypes.byref(pk['head']), U.ptr(qf_d), U.ptr(grid_d), N, T, gh, gw, 256, U.ptr(qp_d), 20.0, ih,
+      iw, U.ptr(o_pts), U.ptr(o_occ), U.ptr(o_exp), U.ptr(o_am), U.ptr(ws), nbytes, U.stream()), 'cv')
+  torch.cuda.synchronize()
+  agree = (o_am.cpu().long() == am[0]).float().mean().item()
+  e_p, e_o, e_e = maxerr(o_pts, pts[0]), maxerr(o_occ, occ[0]), maxerr(o_exp, expd[0])
+  U.record(f'cost_volume_tracks_{gh}x{gw}', argmax_agree=agree, pts_err=e_p, occ_err=e_o, expd_err=e_e)
+  assert agree == 1.0
+  assert e_p < 1e-3 and e_o < 1e-4 and e_e < 1e-4
 
 
 def _run_mixer(model, x, causal, ctx=None, get_ctx=False):
