@@ -291,9 +291,9 @@ def run_offline_workload(R, name, steps, warmup, with_profile=True, legs=('devic
 
   def make_e2e(src_pin):
     def step():
-      v = src_pin.to(dev, non_blocking=True)
-      q = queries_pin.to(dev, non_blocking=True)
-      out = fwd(v, q, True)
+      # the public call with HOST buffers: the clip is streamed to the device in frame chunks
+      # behind the stem convolution (TAPIR.get_feature_grids), queries copied, results read back
+      out = fwd(src_pin, queries_pin, True)
       if rank == 0:
         for k in out_pin:
           out_pin[k].copy_(out[k], non_blocking=True)

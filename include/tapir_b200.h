@@ -221,6 +221,25 @@ int tapir_backbone_forward_u8(const tapir_backbone_weights* w, const uint8_t* vi
                               int32_t frames, int32_t H, int32_t W, float* lowres, float* hires,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same two calls with one more argument: `hires_ready_event` (a cudaEvent_t as void*, or NULL)
+ * is recorded on `stream` as soon as the hires output is final, i.e. before ResNet groups 2-3
+ * and the ExtraConvs run.  The multi-GPU path starts the all-gather of the hires
+ * grid on another stream at that point, hidden behind the rest of the backbone.  video_u8 != 0
+ * selects the uint8 reader. */
+int tapir_backbone_forward_ex(const tapir_backbone_weights* w, const void* video, int32_t video_u8,
+                              int32_t frames, int32_t H, int32_t W, float* lowres, float* hires,
+                              void* workspace, size_t workspace_bytes, void* hires_ready_event,
+                              void* stream);
+
+/* Host-resident clips: the stem convolution (the only reader of the video) of frames
+ * [frame0, frame0 + nframes) of a `pass_frames`-frame backbone pass, run as soon as that chunk
+ * has arrived over PCIe while later chunks are still in flight.  `video_chunk` points at frame
+ * `frame0`.  After every frame of the pass has been through this call (same workspace, same
+ * pass_frames / H / W), tapir_backbone_forward_ex with video == NULL runs the rest. */
+int tapir_backbone_stem(const tapir_backbone_weights* w, const void* video_chunk, int32_t video_u8,
+                        int32_t pass_frames, int32_t H, int32_t W, int32_t frame0, int32_t nframes,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- frame ingest (the step before the path) ------------------------ */
 /* uint8 frames [frames][H][W][3] -> crop window (get_frame's centre square crop,
  * pytorch_live_demo.py:88-95, or any window) -> preprocess_frames (:30-41) -> utils.bilinear

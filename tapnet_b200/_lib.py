@@ -123,6 +123,12 @@ SIGNATURES = {
     'tapir_backbone_forward_u8': (ctypes.c_int, [POINTER(BackboneWeights), c_void_p, c_int32,
                                                  c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                                  c_size_t, c_void_p]),
+    'tapir_backbone_forward_ex': (ctypes.c_int, [POINTER(BackboneWeights), c_void_p, c_int32,
+                                                 c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                                 c_void_p, c_size_t, c_void_p, c_void_p]),
+    'tapir_backbone_stem': (ctypes.c_int, [POINTER(BackboneWeights), c_void_p, c_int32, c_int32,
+                                           c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t,
+                                           c_void_p]),
     'tapir_ingest_frames': (ctypes.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                            c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
     'tapir_postprocess_occlusions': (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p,

@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
       print(out.decode())
   if failed:
     raise RuntimeError('nvcc compilation failed')
-  cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+  cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
   subprocess.check_call(cmd)
   with open(stamp, 'w') as fh:
     fh.write(digest)

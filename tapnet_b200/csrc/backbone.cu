@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) instnorm_finalize_kernel(const double* __
 constexpr int kApplyPixelsPerBlock = 512;
 __global__ void __launch_bounds__(256) instnorm_relu_split_kernel(
     const float* __restrict__ x, const float* __restrict__ mr, long long hw, int C,
-    __nv_bfloat16* __restrict__ out, long long plane_stride, int planes) {
+    __nv_bfloat16* __restrict__ out, long long plane_stride, int planes, int pixels_per_block) {
   const int f = blockIdx.y;
   const int c4n = C / 4;
   const int lanes = 256 / c4n;
@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(256) instnorm_relu_split_kernel(
   const float4 s0 = reinterpret_cast<const float4*>(mr + ((long long)f * C + 4 * g) * 2)[0];
   const float4 s1 = reinterpret_cast<const float4*>(mr + ((long long)f * C + 4 * g) * 2)[1];
   const float sc[4] = {s0.x, s0.z, s1.x, s1.z}, sh[4] = {s0.y, s0.w, s1.y, s1.w};
-  const long long p0 = (long long)blockIdx.x * kApplyPixelsPerBlock;
-  long long p1 = p0 + kApplyPixelsPerBlock;
+  const long long p0 = (long long)blockIdx.x * pixels_per_block;
+  long long p1 = p0 + pixels_per_block;
   if (p1 > hw) p1 = hw;
   const long long base = (long long)f * hw;
   const float4* xin = reinterpret_cast<const float4*>(x);
@@ -429,8 +429,13 @@ int instnorm_relu_split(const float* x, const float* mr, int frames, long long h
                         __nv_bfloat16* out, long long plane_stride, int planes, cudaStream_t s) {
   const long long total4 = (long long)frames * hw * C / 4;
   ProfileScope ps("backbone.instnorm_apply", s, 0.0, (double)total4 * (16 + 8 * planes));
-  dim3 grid((unsigned)ceil_div_ll(hw, kApplyPixelsPerBlock), frames);
-  instnorm_relu_split_kernel<<<grid, 256, 0, s>>>(x, mr, hw, C, out, plane_stride, planes);
+  // single frames (streaming): 512-pixel blocks would give 32 CTAs of 8 dependent load rounds
+  // each; shrink the block until every SM has work (down to one load round per thread)
+  int ppb = kApplyPixelsPerBlock;
+  const int min_ppb = 4 * (256 / (C / 4));
+  while (ppb > min_ppb && ceil_div_ll(hw, ppb) * frames < 2ll * num_sms()) ppb /= 2;
+  dim3 grid((unsigned)ceil_div_ll(hw, ppb), frames);
+  instnorm_relu_split_kernel<<<grid, 256, 0, s>>>(x, mr, hw, C, out, plane_stride, planes, ppb);
   count_launch();
   TAPIR_LAUNCH_CHECK("instnorm_relu_split_kernel");
   return kOk;
@@ -548,11 +553,30 @@ size_t backbone_workspace_bytes(int frames, int H, int W, int extra_convs, int p
   return plan_backbone(a, frames, H, W, extra_convs, planes, &bp) + 256;
 }
 
+int backbone_stem(const tapir_backbone_weights* w, const void* video_chunk, int video_u8,
+                  int pass_frames, int H, int W, int frame0, int nframes, void* ws, size_t ws_bytes,
+                  cudaStream_t s) {
+  TAPIR_CHECK_ARG(w != nullptr && video_chunk != nullptr, "backbone_stem: null pointer");
+  TAPIR_CHECK_ARG(pass_frames > 0 && frame0 >= 0 && nframes > 0 && frame0 + nframes <= pass_frames &&
+                      H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16,
+                  "backbone_stem: bad frame range %d+%d of %d (H=%d W=%d)", frame0, nframes, pass_frames, H, W);
+  Arena arena(ws, ws_bytes);
+  BackbonePlan bp;
+  plan_backbone(arena, pass_frames, H, W, w->num_extra > 0, w->planes, &bp);
+  if (!arena.ok) {
+    set_error("backbone_stem: workspace too small (%zu < %zu)", ws_bytes, arena.off);
+    return kWorkspaceTooSmall;
+  }
+  float* out = bp.buf[0] + (size_t)frame0 * (H / 2) * (W / 2) * 64;
+  return stem_conv(video_chunk, video_u8, w->stem_w, nframes, H, W, out, s);
+}
+
 int backbone_forward(const tapir_backbone_weights* w, const void* video, int video_u8, int frames,
                      int H, int W, float* lowres, float* hires, void* ws, size_t ws_bytes,
-                     cudaStream_t s) {
-  TAPIR_CHECK_ARG(w != nullptr && video != nullptr && lowres != nullptr && hires != nullptr,
-                  "backbone_forward: null pointer");
+                     cudaStream_t s, cudaEvent_t hires_ready) {
+  // video == nullptr: the stem output of all `frames` frames is already in the workspace
+  // (tapir_backbone_stem, called per frame chunk while later chunks are still in flight on PCIe)
+  TAPIR_CHECK_ARG(w != nullptr && lowres != nullptr && hires != nullptr, "backbone_forward: null pointer");
   TAPIR_CHECK_ARG(frames > 0 && H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16,
                   "backbone_forward: image resolution must be a multiple of 8 (H=%d W=%d)", H, W);
   const int P = w->planes;
@@ -567,7 +591,7 @@ int backbone_forward(const tapir_backbone_weights* w, const void* video, int vid
 
   int h = H / 2, wd = W / 2;
   float* x = bp.buf[0];
-  TAPIR_RETURN_IF(stem_conv(video, video_u8, w->stem_w, frames, H, W, x, s));
+  if (video != nullptr) TAPIR_RETURN_IF(stem_conv(video, video_u8, w->stem_w, frames, H, W, x, s));
   int xi = 0;  // index of the buffer holding x
   // InstanceNorm statistics are accumulated by the epilogue of the GEMM that produces the
   // tensor (fp64 atomics into bp.sums); only the stem output needs the stand-alone pass.
@@ -654,6 +678,7 @@ int backbone_forward(const tapir_backbone_weights* w, const void* video, int vid
     (void)m_in;
     if (bi == 3) {  // resnet_unit_1 -> hires (tapir_model.py:356,376-381)
       TAPIR_RETURN_IF(l2_normalize(x, m_out, b.cout, hires, s));
+      if (hires_ready != nullptr) TAPIR_CUDA(cudaEventRecord(hires_ready, s));
     }
   }
   const long long m = (long long)frames * h * wd;

@@ -890,6 +890,16 @@ int launch2(const TcParams& p, const GemmArgs& g, cudaStream_t stream) {
   return kOk;
 }
 
+// Small problems (streaming: one frame, ~1000 mixer rows) cannot fill the GPU with 256-row pair
+// tiles: mixer `down` at 1024 rows is 16 pair tiles = 32 of 148 SMs, each walking all of K.  They
+// take the 1-SM kernel with the narrowest tile that still gives every SM one: 4x the CTAs, each
+// with a quarter of the MMA work per k-block.  (The K-summation order of an output element does
+// not depend on the tile shape, so results stay bit-identical across these choices.)
+bool small_problem(int m_tiles, int N) {
+  const int pairs128 = ((m_tiles + 1) / 2) * ceil_div(N, 128);
+  return 2 * pairs128 * 10 < num_sms() * 6;  // fewer than ~0.6 CTAs per SM as pair tiles
+}
+
 int pick_block_n(int m_tiles, int N, int P) {
   const char* force = getenv("TAPIR_B200_BLOCK_N");
   if (force != nullptr) {
@@ -897,12 +907,8 @@ int pick_block_n(int m_tiles, int N, int P) {
     if (v == 64 || v == 128 || (v == 256 && P <= 2)) return v;
   }
   if (N <= 64) return 64;
-  return 128;  // 256-wide tiles gave no measurable gain (scripts/gemm_bench.py) and spill at 16 epilogue warps
-  // fewest (waves x tile width); 256-wide tiles re-read A half as often, so prefer on ties
-  const int sms = num_sms();
-  const long long c128 = (long long)ceil_div(m_tiles * ceil_div(N, 128), sms) * 128;
-  const long long c256 = (long long)ceil_div(m_tiles * ceil_div(N, 256), sms) * 256;
-  return (c256 <= c128) ? 256 : 128;
+  if (small_problem(m_tiles, N) && m_tiles * ceil_div(N, 128) * 2 <= num_sms()) return 64;
+  return 128;  // 256-wide 1-SM tiles gave no measurable gain (scripts/gemm_bench.py)
 }
 
 }  // namespace
@@ -1002,7 +1008,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   }
 
   // 2-SM path (cta_group::2): pair tiles of 256 x {128, 256}
-  if (use_2sm() != 0 && g.N >= 128 && p.num_m_tiles >= 2 && (num_sms() % 2 == 0)) {
+  if (use_2sm() != 0 && g.N >= 128 && p.num_m_tiles >= 2 && (num_sms() % 2 == 0) &&
+      !small_problem(p.num_m_tiles, g.N)) {
     int bn2 = use_2sm();
     if (bn2 != 128 && bn2 != 256) {
       // auto: the wider tile halves the operand requests but doubles the wave quantum
@@ -1033,11 +1040,13 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   p.split_stride = 0;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = num_sms();
-  // Opt-in (TAPIR_B200_SPLITK=1).  Measured on the streaming step: a GEMM launch has ~12 us of fixed
-  // cost (prologue, pipeline fill, epilogue), so splitting K=2048 saves less than the reduce pass
-  // costs, and it makes results depend on the row count (exact chunk / streaming invariance lost).
+  // On by default (TAPIR_B200_SPLITK=0 disables) for K >= 4096 only: a GEMM launch has ~12 us of
+  // fixed cost, so splitting K = 2048 saves less than the reduce pass costs, but the ExtraConvs'
+  // 1024 -> 256 convolution of ONE frame is 8 row tiles x K = 9216 (56 us on 16 SMs unsplit).  The
+  // summation order then depends on the row count; only problems that cannot half-fill the GPU
+  // split, so offline clips keep their exact chunk / permutation invariance.
   static int splitk_on = -1;
-  if (splitk_on < 0) { const char* e = getenv("TAPIR_B200_SPLITK"); splitk_on = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
+  if (splitk_on < 0) { const char* e = getenv("TAPIR_B200_SPLITK"); splitk_on = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
   if (splitk_on && g.splitk_ws != nullptr && g.stats == nullptr && tiles * 2 <= sms && p.num_k_blocks >= 64) {
     int S = sms / tiles;
     if (S > 8) S = 8;

@@ -46,9 +46,12 @@ int l2_normalize(const float* x, long long rows, int C, float* out, cudaStream_t
 int bilinear_resize(const float* src, int frames, int H, int W, int C, float* dst, int oH, int oW,
                     cudaStream_t s);
 size_t backbone_workspace_bytes(int frames, int H, int W, int extra_convs, int planes);
+int backbone_stem(const tapir_backbone_weights* w, const void* video_chunk, int video_u8,
+                  int pass_frames, int H, int W, int frame0, int nframes, void* ws, size_t ws_bytes,
+                  cudaStream_t s);
 int backbone_forward(const tapir_backbone_weights* w, const void* video, int video_u8, int frames,
                      int H, int W, float* lowres, float* hires, void* ws, size_t ws_bytes,
-                     cudaStream_t s);
+                     cudaStream_t s, cudaEvent_t hires_ready = nullptr);
 
 // ---- callers either side of the path (frames_io.cu) ----------------
 int ingest_frames(const uint8_t* src, int frames, int H, int W, int crop_y, int crop_x, int crop_h,

@@ -275,173 +275,6 @@ __device__ __forceinline__ void ln512(const float4 (&v)[4], const float* __restr
   }
 }
 
-// ---- helpers of mixer_dw_pipe_kernel (below): the phases of mixer_dw_kernel as functions.  The
-// validated kernel keeps its own inline copy until the pipelined variant has run on a GPU; then
-// both should share these.
-// Per-channel weights of the two depthwise convs (thread = channel c, 4 multipliers).
-struct DwWeights {
-  float w1[4][3], w2[4][3], b1[4], b2[4];
-};
-
-__device__ __forceinline__ void dw_load_weights(const DwParams& p, int c, DwWeights& k) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    k.b1[j] = p.b1[4 * c + j];
-    k.b2[j] = p.b2[4 * c + j];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      k.w1[j][i] = p.w1[(4 * c + j) * 3 + i];
-      k.w2[j][i] = p.w2[(4 * c + j) * 3 + i];
-    }
-  }
-}
-
-// Phase 1 for one row: frame t of query n -> LN(x) * w (or causal context / zero padding) in
-// `dst`; `xr` is the raw row (global or staged shared memory), `xkeep` (nullable) receives a copy
-// of the raw row for the skip connection.
-template <bool CAUSAL>
-__device__ __forceinline__ void dw_norm_row(const DwParams& p, int n, int t, int T, const float4* xr,
-                                            float4* dst, float4* xkeep, int lane) {
-  if (t >= 0 && t < T) {
-    float4 v[4], o[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = xr[i * 32 + lane];
-    ln512(v, p.ln_w, lane, o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i * 32 + lane] = o[i];
-    if (xkeep != nullptr) {  // the frame loop must not wait on L2 for the skip input
-#pragma unroll
-      for (int i = 0; i < 4; ++i) xkeep[i * 32 + lane] = v[i];
-    }
-  } else if (CAUSAL && p.ctx1_in != nullptr && t >= -2 && t < 0) {
-    // context frames -2, -1 of the layer-normed input (nets.py:149-153)
-    const float4* cr = reinterpret_cast<const float4*>(p.ctx1_in + ((long long)n * 2 + (t + 2)) * 512);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i * 32 + lane] = cr[i * 32 + lane];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i * 32 + lane] = make_float4(0, 0, 0, 0);
-  }
-}
-
-// Phase 2 for one query and one channel: both depthwise convs + GELU + group sum + skip over
-// the output frames t0 .. t1-1.  yq = this channel's column of the query's layer-normed rows
-// (row r <-> frame lo + r; rows are recycled for z), xq = column of the raw rows of frames t0..
-template <bool CAUSAL>
-__device__ __forceinline__ void dw_frames(const DwParams& p, const DwWeights& k, int n, float* yq,
-                                          const float* xq, int t0, int t1, int lo, int c) {
-  const int T = p.T;
-  // h1 of frame f = first + j is a function of smem rows j, j+1, j+2 (both modes)
-  const int first = CAUSAL ? t0 - 2 : t0 - 1;
-  if (CAUSAL && p.ctx1_out != nullptr) {
-    // new context of the layer-normed input: last two frames of [ctx | y] (nets.py:153);
-    // written before the rows are recycled for z
-    for (int t = max(t0, T - 2); t < t1; ++t)
-      p.ctx1_out[((long long)n * 2 + (t - (T - 2))) * 512 + c] = yq[(t - lo) * 512];
-    // clip shorter than the context: slot 0 <- old frame -1, which phase 1 staged in row 3
-    // (frame -1) of this query; reading the staged copy (not ctx1_in) keeps the update correct
-    // when the caller passes the SAME buffers as context in and out (streaming, T = 1)
-    if (T == 1 && t0 == 0) p.ctx1_out[((long long)n * 2) * 512 + c] = yq[3 * 512];
-  }
-  float y0 = yq[0], y1 = yq[512];
-  float ha[4], hb[4], hc[4];
-  // h1 of frame f = first + j.  The tested form handles sequence ends (zero padding / causal
-  // context / context output); the untested form is the same arithmetic without the tests, so a
-  // frame gives the same bits whichever form computes it (chunk invariance stays exact).
-  auto h1_math = [&](float y2, float (&o)[4]) {
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-      o[m] = gelu_tanh(fmaf(k.w1[m][2], y2, fmaf(k.w1[m][1], y1, fmaf(k.w1[m][0], y0, k.b1[m]))));
-  };
-  auto h1 = [&](int j, float (&o)[4]) {
-    const int f = first + j;
-    const float y2 = yq[(j + 2) * 512];
-    if (f >= 0 && f < T) {
-      h1_math(y2, o);
-      if (CAUSAL && p.ctx2_out != nullptr && f >= T - 2)  // last two frames of [ctx | h1] (nets.py:167)
-        *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + (f - (T - 2))) * 2048 + 4 * c) =
-            make_float4(o[0], o[1], o[2], o[3]);
-    } else if (CAUSAL && p.ctx2_in != nullptr && f >= -2 && f < 0) {
-      const float4 v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + (f + 2)) * 2048 + 4 * c);
-      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    } else {
-      o[0] = o[1] = o[2] = o[3] = 0.f;  // zero padding of the second conv's input
-    }
-    y0 = y1;
-    y1 = y2;
-  };
-  // second conv + group sum + skip for output frame i, from h1 of frames i-1, i, i+1 (a, b, c);
-  // rows <= i + 2 of this column are dead by then: z[t0 + i] is parked in row i
-  auto emit = [&](float* yrow, const float* xrow, float* zrow, const float (&a)[4],
-                  const float (&b)[4], const float (&cc)[4]) {
-    float acc = *xrow;
-#pragma unroll
-    for (int m = 0; m < 4; ++m)
-      acc += fmaf(k.w2[m][2], cc[m], fmaf(k.w2[m][1], b[m], fmaf(k.w2[m][0], a[m], k.b2[m])));
-    *yrow = acc;
-    *zrow = acc;
-  };
-  h1(0, ha);
-  h1(1, hb);
-  // T = 1: hb is h1 of frame -1 (old context slot 1, or zero); it becomes slot 0 of the new
-  // context.  Written only now, after both old slots were read (in/out buffers may alias).
-  if (CAUSAL && p.ctx2_out != nullptr && T == 1 && t0 == 0)
-    *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2) * 2048 + 4 * c) =
-        make_float4(hb[0], hb[1], hb[2], hb[3]);
-  const int nout = t1 - t0;
-  // output frames whose newest h1 frame (first + i + 2) needs no end-of-sequence handling
-  int i_lo = max(0, -(first + 2));
-  int i_hi = min(nout, ((CAUSAL && p.ctx2_out != nullptr) ? T - 2 : T) - (first + 2));
-  if (i_hi < i_lo) i_lo = i_hi = 0;
-  float* yp = yq;
-  const float* xp = xq;
-  float* zp = p.z + ((long long)n * T + t0) * 512 + c;
-  int i = 0;
-  auto checked_until = [&](int stop) {
-    for (; i < stop; ++i, yp += 512, xp += 512, zp += 512) {
-      h1(i + 2, hc);
-      emit(yp, xp, zp, ha, hb, hc);
-#pragma unroll
-      for (int m = 0; m < 4; ++m) { ha[m] = hb[m]; hb[m] = hc[m]; }
-    }
-  };
-  checked_until(i_lo);
-  // interior, three frames per trip: the roles of (ha, hb, hc) rotate back after three steps,
-  // so no register moves and no tests
-  for (; i + 3 <= i_hi; i += 3, yp += 1536, xp += 1536, zp += 1536) {
-    const float ya = yp[4 * 512], yb = yp[5 * 512], yc = yp[6 * 512];
-    h1_math(ya, hc);
-    y0 = y1; y1 = ya;
-    emit(yp, xp, zp, ha, hb, hc);
-    h1_math(yb, ha);
-    y0 = y1; y1 = yb;
-    emit(yp + 512, xp + 512, zp + 512, hb, hc, ha);
-    h1_math(yc, hb);
-    y0 = y1; y1 = yc;
-    emit(yp + 1024, xp + 1024, zp + 1024, hc, ha, hb);
-  }
-  checked_until(nout);
-}
-
-// Phase 3 for one row: LN_1(z) * w (scale only) -> bf16 planes, the A operand of the `up` GEMM.
-__device__ __forceinline__ void dw_planes_row(const DwParams& p, const float4* zr, long long orow,
-                                              int lane) {
-  float4 v[4], o4[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) v[k] = zr[k * 32 + lane];
-  ln512(v, p.ln1_w, lane, o4);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    float o[4] = {o4[k].x, o4[k].y, o4[k].z, o4[k].w};
-    for (int pl = 0; pl < p.planes; ++pl) {
-      uint2 pk;
-      pk.x = bf16x2_split(o[0], o[1]);
-      pk.y = bf16x2_split(o[2], o[3]);
-      *reinterpret_cast<uint2*>(p.planes_out + pl * p.plane_stride + orow * 512 + (k * 32 + lane) * 4) = pk;
-    }
-  }
-}
-
 template <bool CAUSAL>
 __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
   extern __shared__ float dw_smem[];
@@ -503,15 +336,33 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
   }
   // h1 of frame f = first + j is a function of smem rows j, j+1, j+2 (both modes)
   const int first = CAUSAL ? t0 - 2 : t0 - 1;
+  // Causal context of the hidden activation (frames -2, -1 of h1; only the first tile of a clip
+  // reads it).  The values of query q + 1 are fetched while query q is computed: with several
+  // queries per CTA (short clips, streaming) three dependent global loads per query used to
+  // serialise - 8 queries x 3 x ~0.7 us was most of the 23 us a T = 1 launch took.
+  const bool has_ctx2 = CAUSAL && p.ctx2_in != nullptr && t0 == 0;
+  float4 ctx_next[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
+  auto fetch_ctx2 = [&](int q) {
+    if (has_ctx2 && q < nq) {
+      const float* src = p.ctx2_in + ((long long)(n0 + q) * 2) * 2048 + 4 * c;
+      ctx_next[0] = *reinterpret_cast<const float4*>(src);
+      ctx_next[1] = *reinterpret_cast<const float4*>(src + 2048);
+    }
+  };
+  fetch_ctx2(0);
   for (int q = 0; q < nq; ++q) {
     const int n = n0 + q;
     float* yq = ybuf + q * RY * 512 + c;
+    const float4 ctx_cur[2] = {ctx_next[0], ctx_next[1]};
+    fetch_ctx2(q + 1);
     if (CAUSAL && p.ctx1_out != nullptr) {
       // new context of the layer-normed input: last two frames of [ctx | y] (nets.py:153);
       // written before the rows are recycled for z
       for (int t = max(t0, T - 2); t < t1; ++t)
         p.ctx1_out[((long long)n * 2 + (t - (T - 2))) * 512 + c] = yq[(t - lo) * 512];
-      // clip shorter than the context: slot 0 <- old frame -1 = staged row 3 (see dw_frames)
+      // clip shorter than the context: slot 0 <- old frame -1, which phase 1 staged in row 3
+      // (frame -1) of this query; reading the staged copy (not ctx1_in) keeps the update correct
+      // when the caller passes the SAME buffers as context in and out (streaming, T = 1)
       if (T == 1 && t0 == 0) p.ctx1_out[((long long)n * 2) * 512 + c] = yq[3 * 512];
     }
     float y0 = yq[0], y1 = yq[512];
@@ -532,8 +383,8 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
         if (CAUSAL && p.ctx2_out != nullptr && f >= T - 2)  // last two frames of [ctx | h1] (nets.py:167)
           *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + (f - (T - 2))) * 2048 + 4 * c) =
               make_float4(o[0], o[1], o[2], o[3]);
-      } else if (CAUSAL && p.ctx2_in != nullptr && f >= -2 && f < 0) {
-        const float4 v = *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + (f + 2)) * 2048 + 4 * c);
+      } else if (has_ctx2 && f >= -2 && f < 0) {
+        const float4 v = (f == -2) ? ctx_cur[0] : ctx_cur[1];
         o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
       } else {
         o[0] = o[1] = o[2] = o[3] = 0.f;  // zero padding of the second conv's input
@@ -554,7 +405,9 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
     };
     h1(0, ha);
     h1(1, hb);
-    if (CAUSAL && p.ctx2_out != nullptr && T == 1 && t0 == 0)  // see dw_frames
+    // T = 1: hb is h1 of frame -1 (old context slot 1, or zero); it becomes slot 0 of the new
+    // context.  Written only now, after both old slots were read (in/out buffers may alias).
+    if (CAUSAL && p.ctx2_out != nullptr && T == 1 && t0 == 0)
       *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2) * 2048 + 4 * c) =
           make_float4(hb[0], hb[1], hb[2], hb[3]);
     const int nout = t1 - t0;
@@ -613,97 +466,6 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
         *reinterpret_cast<uint2*>(p.planes_out + pl * p.plane_stride + orow * 512 + (k * 32 + lane) * 4) = pk;
       }
     }
-  }
-}
-
-// Long clips with many queries (the 4096-query regime): the working set of a launch exceeds L2
-// and the kernel above is HBM-latency bound, because rows are in flight only during its phase 1
-// (DESIGN.md 8.2).  Here CTAs are persistent, one query x 12 frames per work item, and the raw
-// rows of the NEXT work item stream into a second staging buffer (cp.async.bulk, 2 KB per row,
-// completion on an mbarrier) while the current item is in phases 1-3.  Same arithmetic, same
-// helper functions: results are bit-identical to mixer_dw_kernel.  OPT-IN (TAPIR_B200_DW_PIPE=1)
-// until it has been validated and measured on a GPU.
-// Non-tensor bulk copy global -> shared (contiguous bytes; 16-byte aligned, multiple of 16),
-// completion counted on an mbarrier like a tensor TMA load.  (Lives here, not in ptx.cuh, so the
-// GEMM translation unit stays byte-identical to the validated build.)
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes,
-                                              uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          ptx::smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(ptx::smem_u32(bar))
-      : "memory");
-}
-
-constexpr int kDwPipeTile = 12;                       // output frames per work item
-constexpr int kDwPipeRows = kDwPipeTile + kDwHalo;    // 16 rows per buffer
-constexpr int kDwPipeSmem = 3 * kDwPipeRows * 512 * (int)sizeof(float) + 64;  // y + 2 stages + barriers
-
-template <bool CAUSAL>
-__global__ void __launch_bounds__(512, 2) mixer_dw_pipe_kernel(const DwParams p, int* err) {
-  extern __shared__ __align__(128) float dw_smem[];
-  float* ybuf = dw_smem;                                    // [16][512]
-  float* stage0 = dw_smem + kDwPipeRows * 512;              // [2][16][512] raw rows
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dw_smem + 3 * kDwPipeRows * 512);
-  const int T = p.T;
-  const int tiles = (T + kDwPipeTile - 1) / kDwPipeTile;
-  const long long items = (long long)p.N * tiles;
-  const int c = threadIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    ptx::mbar_init(&bars[0], 1);
-    ptx::mbar_init(&bars[1], 1);
-    ptx::fence_barrier_init();
-  }
-  __syncthreads();
-  DwWeights k;
-  dw_load_weights(p, c, k);
-
-  // raw rows of work item `w` -> stage buffer `b` (one elected thread; rows outside the clip are
-  // not loaded - phase 1 replaces them by context / zeros)
-  auto prefetch = [&](long long w, int b) {
-    const int n = (int)(w / tiles);
-    const int t0 = (int)(w - (long long)n * tiles) * kDwPipeTile;
-    const int t1 = min(t0 + kDwPipeTile, T);
-    const int lo = CAUSAL ? t0 - 4 : t0 - 2;
-    const int hi = CAUSAL ? t1 : t1 + 2;
-    const int a = max(lo, 0), e = min(hi, T);
-    ptx::fence_proxy_async();  // earlier generic reads of this buffer happen before the async writes
-    ptx::mbar_arrive_expect_tx(&bars[b], (uint32_t)(e - a) * 2048u);
-    for (int t = a; t < e; ++t)
-      bulk_copy_g2s(stage0 + (b * kDwPipeRows + (t - lo)) * 512,
-                         p.x + ((long long)n * T + t) * 512, 2048u, &bars[b]);
-  };
-
-  long long w = blockIdx.x;
-  if (w < items && threadIdx.x == 0) prefetch(w, 0);
-  int it = 0;
-  for (; w < items; w += gridDim.x, ++it) {
-    const int b = it & 1;
-    const uint32_t parity = (uint32_t)(it >> 1) & 1u;
-    const int n = (int)(w / tiles);
-    const int t0 = (int)(w - (long long)n * tiles) * kDwPipeTile;
-    const int t1 = min(t0 + kDwPipeTile, T);
-    const int lo = CAUSAL ? t0 - 4 : t0 - 2;
-    const int nrow = (CAUSAL ? t1 : t1 + 2) - lo;
-    float* stage = stage0 + b * kDwPipeRows * 512;
-    // the other buffer was last read in the previous iteration (all threads are past its final
-    // __syncthreads), so the next item's rows may start streaming into it now
-    if (threadIdx.x == 0 && w + gridDim.x < items) prefetch(w + gridDim.x, b ^ 1);
-    ptx::mbar_wait(&bars[b], parity, err, 301);
-
-    // ---- phase 1 (rows come from the staging buffer)
-    for (int r = warp; r < nrow; r += 16)
-      dw_norm_row<CAUSAL>(p, n, lo + r, T, reinterpret_cast<const float4*>(stage + r * 512),
-                          reinterpret_cast<float4*>(ybuf + r * 512), nullptr, lane);
-    __syncthreads();
-    // ---- phase 2 (skip input: raw rows of frames t0.. straight from the staging buffer)
-    dw_frames<CAUSAL>(p, k, n, ybuf + c, stage + (t0 - lo) * 512 + c, t0, t1, lo, c);
-    __syncthreads();
-    // ---- phase 3
-    for (int i = warp; i < t1 - t0; i += 16)
-      dw_planes_row(p, reinterpret_cast<const float4*>(ybuf + i * 512), (long long)n * T + t0 + i, lane);
-    __syncthreads();  // ybuf and this staging buffer are free for the next iterations
   }
 }
 
@@ -828,19 +590,6 @@ GemmArgs lin(const tapir_linear& l) {
 }
 }  // namespace
 
-// TAPIR_B200_DW_PIPE: 0 / unset = mixer_dw_kernel everywhere (default, the validated path);
-// 1 = mixer_dw_pipe_kernel for launches whose working set exceeds L2; 2 = for every launch
-// (bring-up: lets the whole parity suite exercise it).  Not yet validated on a GPU.
-int use_dw_pipe() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TAPIR_B200_DW_PIPE");
-    v = (e != nullptr) ? atoi(e) : 0;
-    if (v < 0 || v > 2) v = 0;
-  }
-  return v;
-}
-
 size_t mixer_workspace_bytes(long long rows, int planes) {
   Arena a(nullptr, 0);
   MixerPlan m;
@@ -869,10 +618,6 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     const int max_smem = kDwRowBudget * 512 * (int)sizeof(float);
     TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    if (use_dw_pipe() != 0) {
-      TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwPipeSmem));
-      TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwPipeSmem));
-    }
     configured.mark();
   }
   {  // nets.py:235 linear
@@ -896,6 +641,8 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     d.QB = kDwRowBudget / (2 * d.TT + kDwHalo);
     if (d.QB < 1) d.QB = 1;
     if (d.QB > 8) d.QB = 8;
+    // few rows in total (streaming): fewer queries per CTA so that every SM gets one
+    while (d.QB > 1 && (long long)ceil_div(n, d.QB) * ceil_div(T, d.TT) < 2ll * num_sms()) d.QB /= 2;
     if (d.QB > n) d.QB = n;
     d.ln_w = blk.ln_w; d.w1 = blk.dw1_w; d.b1 = blk.dw1_b; d.w2 = blk.dw2_w; d.b2 = blk.dw2_b;
     d.ln1_w = blk.ln1_w;
@@ -905,19 +652,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     d.ctx2_out = io->ctx2_out ? io->ctx2_out[b] : nullptr;
     dim3 grid(ceil_div(T, d.TT), ceil_div(n, d.QB));
     const int dw_smem = d.QB * (2 * d.TT + kDwHalo) * 512 * (int)sizeof(float);
-    if (use_dw_pipe() == 2 ||
-        (use_dw_pipe() == 1 && T >= 2 * kDwPipeTile && rows * 512 * 4 * 3 > (64ll << 20))) {
-      // opt-in: persistent, cross-tile prefetching variant for launches whose working set
-      // (x, z, planes) does not fit L2
-      const long long items = (long long)n * ceil_div(T, kDwPipeTile);
-      const int ctas = (int)(items < 2ll * num_sms() ? items : 2ll * num_sms());
-      ProfileScope ps("mixer.dw", s, (double)rows * 2048 * 12, (double)rows * 512 * (8 + 2 * P));
-      if (io->causal) {
-        mixer_dw_pipe_kernel<true><<<ctas, 512, kDwPipeSmem, s>>>(d, nullptr);
-      } else {
-        mixer_dw_pipe_kernel<false><<<ctas, 512, kDwPipeSmem, s>>>(d, nullptr);
-      }
-    } else {
+    {
       ProfileScope ps("mixer.dw", s, (double)rows * 2048 * 12, (double)rows * 512 * (8 + 2 * P));
       if (io->causal) {
         mixer_dw_kernel<true><<<grid, 512, dw_smem, s>>>(d);

@@ -27,18 +27,36 @@ def query_shard(num_queries: int, rank: int, world: int) -> Tuple[int, int]:
   return start, min(start + per, num_queries)
 
 
-def all_gather_frames(local: torch.Tensor, num_frames: int, group=None) -> torch.Tensor:
-  """local: [B, t_local, ...] (this rank's frame slice) -> [B, num_frames, ...] on every rank."""
+def all_gather_frames(local: torch.Tensor, num_frames: int, group=None, async_op: bool = False):
+  """local: [B, t_local, ...] (this rank's frame slice) -> [B, num_frames, ...] on every rank.
+
+  B == 1 (every demo / benchmark): `[1, t, ...]` IS `[t, ...]` in memory, so the ranks' slices
+  are gathered straight into the final layout - no transpose, no zero fill, no copy (the short
+  last rank, when the frames do not divide evenly, sends from a padded staging buffer).  With
+  async_op the call returns (tensor, work); the tensor is valid after work.wait()."""
   world = dist.get_world_size(group)
   rank = dist.get_rank(group)
   _, _, per = frame_shard(num_frames, rank, world)
   b = local.shape[0]
   rest = tuple(local.shape[2:])
+  if b == 1:
+    send = local[0].contiguous()
+    if send.shape[0] != per:  # short (or empty) last rank
+      pad = local.new_zeros((per,) + rest)
+      pad[:send.shape[0]] = send
+      send = pad
+    out = local.new_empty((1, world * per) + rest)
+    work = dist.all_gather_into_tensor(out[0], send, group=group, async_op=async_op)
+    res = out[:, :num_frames]  # a prefix of the frame axis: still contiguous for B == 1
+    return (res, work) if async_op else res
   send = local.new_zeros((per, b) + rest)
   send[:local.shape[1]] = local.transpose(0, 1)
   out = local.new_empty((world * per, b) + rest)
-  dist.all_gather_into_tensor(out, send.contiguous(), group=group)
-  return out[:num_frames].transpose(0, 1).contiguous()
+  work = dist.all_gather_into_tensor(out, send.contiguous(), group=group, async_op=async_op)
+  if async_op:
+    work.wait()
+  res = out[:num_frames].transpose(0, 1).contiguous()
+  return (res, None) if async_op else res
 
 
 def gather_queries(local: torch.Tensor, num_queries: int, dim: int = 1, group=None) -> torch.Tensor:
@@ -51,6 +69,16 @@ def gather_queries(local: torch.Tensor, num_queries: int, dim: int = 1, group=No
   out = x.new_empty((world * per,) + tuple(x.shape[1:]))
   dist.all_gather_into_tensor(out, send, group=group)
   return out[:num_queries].transpose(0, dim).contiguous()
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+  key = str(device)
+  if key not in _SIDE_STREAMS:
+    _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+  return _SIDE_STREAMS[key]
 
 
 def sharded_forward(model, video: torch.Tensor, query_points: torch.Tensor, gather_outputs=True,
@@ -67,22 +95,60 @@ def sharded_forward(model, video: torch.Tensor, query_points: torch.Tensor, gath
   T = video.shape[1]
   N = query_points.shape[1]
   f0, f1, _ = frame_shard(T, rank, world)
+  mdev = next(model.parameters()).device
+  on_gpu = mdev.type == 'cuda'
+  if on_gpu and query_points.device.type == 'cpu':
+    # host buffers in: each rank copies only its own frames (get_feature_grids streams them)
+    query_points = query_points.to(mdev, non_blocking=True)
+  hires_events = []
   if f1 > f0:
-    local = model.get_feature_grids(video[:, f0:f1], False)
+    local = model.get_feature_grids(video[:, f0:f1], False, hires_ready_events=hires_events)
     lo_l, hi_l, res = list(local.lowres), list(local.hires), local.resolutions
   else:  # more ranks than frames: contribute an empty slice with the right trailing shape
     probe = model.get_feature_grids(video[:, :1], False)
     lo_l = [t[:, :0] for t in probe.lowres]
     hi_l = [t[:, :0] for t in probe.hires]
     res = probe.resolutions
-  lowres, hires = [], []
-  cache = {}
+  # The hires grid of a resolution is final one third of the way through its backbone pass: its
+  # all-gather is issued behind the `hires ready` event on a side stream, so NCCL moves it while
+  # ResNet groups 2-3 and the ExtraConvs are still running.  Only the lowres
+  # gather, which needs the end of the backbone, stays exposed.  Every rank issues the
+  # collectives in the same order (hires of each distinct resolution, then lowres of each).
+  main = torch.cuda.current_stream(mdev) if on_gpu else None
+  ready = {h.data_ptr(): ev for h, ev in hires_events}
+  side = _side_stream(mdev) if on_gpu else None
+  pending_hi, pending_lo, order = {}, {}, []
   for lo, hi in zip(lo_l, hi_l):
     key = (lo.data_ptr(), hi.data_ptr())
-    if key not in cache:  # equal resolutions alias one tensor: gather it once
-      cache[key] = (all_gather_frames(lo, T, group), all_gather_frames(hi, T, group))
-    lowres.append(cache[key][0])
-    hires.append(cache[key][1])
+    if key in pending_hi:  # equal resolutions alias one tensor: gather it once
+      order.append(key)
+      continue
+    ev = ready.get(hi.data_ptr())
+    if side is not None and ev is not None:
+      side.wait_event(ev)
+      with torch.cuda.stream(side):
+        pending_hi[key] = all_gather_frames(hi, T, group, async_op=True)
+      hi.record_stream(side)
+    else:
+      pending_hi[key] = all_gather_frames(hi, T, group, async_op=True)
+    order.append(key)
+  for lo, hi in zip(lo_l, hi_l):
+    key = (lo.data_ptr(), hi.data_ptr())
+    if key not in pending_lo:
+      pending_lo[key] = all_gather_frames(lo, T, group, async_op=True)
+  lowres, hires = [], []
+  for key in order:
+    for pend in (pending_lo, pending_hi):
+      t, work = pend[key]
+      if work is not None:
+        if main is not None:
+          with torch.cuda.stream(main):
+            work.wait()
+        else:
+          work.wait()
+        pend[key] = (t, None)
+    lowres.append(pending_lo[key][0])
+    hires.append(pending_hi[key][0])
   grids = FeatureGrids(tuple(lowres), tuple(hires), tuple(res))
   q0, q1 = query_shard(N, rank, world)
   qp = query_points[:, q0:q1]

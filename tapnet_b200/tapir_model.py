@@ -74,6 +74,8 @@ _PRECISIONS = {'bf16': 1, 'bf16x3': 2, 'bf16x6': 3}
 _MAX_ROWS_PER_CHUNK = 98304
 # input pixels (frames x H x W) per backbone pass; bounds the workspace to ~2.7 GB
 _MAX_BACKBONE_PIXELS = 96 * 256 * 256
+# host clips: H2D sub-chunks per backbone pass (each followed by its stem-conv launch)
+_H2D_SUBCHUNKS = 6
 
 
 def _ptr(t):
@@ -154,6 +156,7 @@ class TAPIR(nn.Module):
     self._packed = None
     self._packed_sig = None
     self._ws = {}
+    self._copy_streams = {}
     self._ws_retired = []
     self._ws_pins = 0
     self._ws_generation = 0
@@ -203,6 +206,12 @@ class TAPIR(nn.Module):
     # the current stream OF THE MODEL'S DEVICE (every public method runs its launches inside
     # `torch.cuda.device(dev)`, so the C side's per-device caches and the pointers agree)
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+  def _copy_stream(self, dev):
+    key = str(dev)
+    if key not in self._copy_streams:
+      self._copy_streams[key] = torch.cuda.Stream(device=dev)
+    return self._copy_streams[key]
 
   def _const(self, values, dev):
     """Small constant vectors, cached: creating them per call costs a blocking H2D copy."""
@@ -342,6 +351,10 @@ class TAPIR(nn.Module):
     """Reference tapir_model.py:139-215."""
     if get_query_feats:
       raise ValueError('Get query feats not supported in TAPIR.')
+    pdev = next(self.parameters()).device
+    if pdev.type == 'cuda' and video.device.type == 'cpu' and query_points.device.type == 'cpu':
+      # host buffers in (extension): the clip is streamed in by get_feature_grids
+      query_points = query_points.to(pdev, non_blocking=True)
     feature_grids = self.get_feature_grids(video, is_training, refinement_resolutions)
     query_features = self.get_query_features(video, is_training, query_points, feature_grids,
                                              refinement_resolutions)
@@ -363,8 +376,13 @@ class TAPIR(nn.Module):
       video: torch.Tensor,
       is_training: bool,
       refinement_resolutions: Optional[List[Tuple[int, int]]] = None,
+      hires_ready_events: Optional[list] = None,
   ) -> FeatureGrids:
-    """Reference tapir_model.py:293-392.  video: [B, T, H, W, 3] float in [-1, 1]."""
+    """Reference tapir_model.py:293-392.  video: [B, T, H, W, 3] float in [-1, 1].
+
+    `hires_ready_events` (extension, used by tapnet_b200.distributed): a list that receives one
+    (hires tensor, torch.cuda.Event) pair per distinct resolution; the event fires as soon as
+    that hires grid is final, while ResNet groups 2-3 and the ExtraConvs are still running."""
     del is_training
     if refinement_resolutions is None:
       refinement_resolutions = generate_default_resolutions(video.shape[2:4],
@@ -373,7 +391,11 @@ class TAPIR(nn.Module):
     for resolution in all_required:
       if resolution[0] % 8 != 0 or resolution[1] % 8 != 0:
         raise ValueError('Image resolution must be a multiple of 8.')
-    dev = self._device_check(video)
+    # A HOST clip (ideally pinned) is accepted too (extension): its frames are copied to the
+    # device in chunks on a copy stream and the stem convolution - the only reader of the video -
+    # runs chunk by chunk behind them, so PCIe time hides behind compute.
+    host_video = video.device.type == 'cpu'
+    dev = self._device_check(None if host_video else video)
     lib = _lib.load()
     pk = self._pack()
     # uint8 video = raw [0,255] frames (what the reference's callers hold before
@@ -383,6 +405,14 @@ class TAPIR(nn.Module):
     video_u8 = video.dtype == torch.uint8
     video = video.contiguous() if video_u8 else video.to(torch.float32).contiguous()
     n, f, vh, vw, _ = video.shape
+    host_src = None
+    if host_video:
+      host_src = video
+      video = torch.empty(video.shape, dtype=video.dtype, device=dev)
+      if tuple(all_required[0]) != (vh, vw):
+        # the first pass resizes the clip: it needs all of it on the device up front
+        video.copy_(host_src, non_blocking=True)
+        host_src = None
     feature_grid, hires_feats, resize_im_shape = [], [], []
     curr_resolution = (-1, -1)
     latent = hires = None
@@ -427,13 +457,40 @@ class TAPIR(nn.Module):
         chunk = min(chunk, nf)
         nbytes = lib.tapir_backbone_workspace_bytes(chunk, h, w, int(self._has_extra), self._planes)
         ws = self._workspace('backbone', nbytes, dev)
+        ev = None
+        if hires_ready_events is not None:
+          ev = torch.cuda.Event()
+          ev.record(torch.cuda.current_stream(dev))  # materialises the CUDA event handle
+          hires_ready_events.append((hires, ev))
+        streamed = host_src is not None and frames_src is video
+        if streamed:
+          main = torch.cuda.current_stream(dev)
+          cs = self._copy_stream(dev)
+          cs.wait_stream(main)  # the staging buffer's previous owner is done
+          host_flat = host_src.view(nf, h, w, 3)
         for s0 in range(0, nf, chunk):
           c = min(chunk, nf - s0)
-          fwd = (lib.tapir_backbone_forward_u8 if flat_src.dtype == torch.uint8
-                 else lib.tapir_backbone_forward)
-          _lib.check(fwd(ctypes.byref(pk['backbone']), _ptr(flat_src[s0:]), c, h, w,
-                         _ptr(flat_lo[s0:]), _ptr(flat_hi[s0:]), _ptr(ws), ws.numel(), stream),
+          last = s0 + c >= nf
+          if streamed:
+            sub = max(1, -(-c // _H2D_SUBCHUNKS))
+            for a in range(s0, s0 + c, sub):
+              b = min(a + sub, s0 + c)
+              with torch.cuda.stream(cs):
+                flat_src[a:b].copy_(host_flat[a:b], non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record(cs)
+              main.wait_event(arrived)
+              _lib.check(lib.tapir_backbone_stem(
+                  ctypes.byref(pk['backbone']), _ptr(flat_src[a:]), int(video_u8), c, h, w, a - s0,
+                  b - a, _ptr(ws), ws.numel(), stream), 'tapir_backbone_stem')
+          _lib.check(lib.tapir_backbone_forward_ex(
+              ctypes.byref(pk['backbone']), None if streamed else _ptr(flat_src[s0:]),
+              int(flat_src.dtype == torch.uint8),
+              c, h, w, _ptr(flat_lo[s0:]), _ptr(flat_hi[s0:]), _ptr(ws), ws.numel(),
+              ctypes.c_void_p(ev.cuda_event) if (ev is not None and last) else None, stream),
                      'tapir_backbone_forward')
+        if streamed:
+          host_src = None  # the whole clip is on the device now (later passes resize from it)
       feature_grid.append(latent)
       hires_feats.append(hires)
       resize_im_shape.append(torch.Size(shape_hw))

@@ -237,3 +237,27 @@ def test_tracker_survives_workspace_growth():
   a, b = run(False), run(True)
   assert torch.equal(a, b)
   U.record('tracker_workspace_growth', equal=1)
+
+
+def test_host_clip_streamed_in_equals_device_clip():
+  """model(host video, host queries): the clip is copied in frame chunks behind the stem conv;
+  results must equal the device-resident call bit for bit (float and uint8 clips)."""
+  model, _, _ = get_model()
+  T, N = 13, 24   # 13 frames: ragged sub-chunks
+  video = synth.make_video(T)
+  q = synth.make_queries(N, T)
+  ref = model(video.cuda(), q.cuda())
+  got = model(video.pin_memory(), q.pin_memory())
+  assert torch.equal(ref['tracks'], got['tracks']) and torch.equal(ref['occlusion'], got['occlusion'])
+  u8 = ((video + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)
+  ref8 = model(u8.cuda(), q.cuda())
+  got8 = model(u8.pin_memory(), q)   # pageable queries are fine too
+  assert torch.equal(ref8['tracks'], got8['tracks'])
+  assert torch.equal(ref8['expected_dist'], got8['expected_dist'])
+  # a clip whose first pass resizes (480 -> 256) takes the copy-everything-first route
+  v480 = synth.make_video(2, 480, 480)
+  q480 = synth.make_queries(6, 2, 480, 480)
+  a = model(v480.cuda(), q480.cuda())
+  b = model(v480.pin_memory(), q480.pin_memory())
+  assert torch.equal(a['tracks'], b['tracks'])
+  U.record('host_clip_streaming', equal=1)
