@@ -1,4 +1,5 @@
-"""Runs `--warm` warm-up steps + `--steps` steps of the bench workload (for ncu captures)."""
+"""Runs `--warm` warm-up steps + `--steps` steps of an offline workload (for ncu captures).
+Default = the bench headline (BASELINE config 2: 256x256x48, 256 queries)."""
 import argparse
 import os
 import sys
@@ -7,21 +8,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-import bench  # noqa: E402
-from tapnet_b200 import tapir_model  # noqa: E402
+from tapnet_b200 import synth, tapir_model  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--warm', type=int, default=2)
 ap.add_argument('--steps', type=int, default=1)
-ap.add_argument('--frames', type=int, default=bench.T_FRAMES)
-ap.add_argument('--queries', type=int, default=bench.Q_PER_GPU)
+ap.add_argument('--frames', type=int, default=48)
+ap.add_argument('--queries', type=int, default=256)
+ap.add_argument('--res', type=int, default=256)
 a = ap.parse_args()
-bench.T_FRAMES, bench.Q_PER_GPU = a.frames, a.queries
-sd, video, queries = bench.build_inputs(1)
 model = tapir_model.TAPIR(pyramid_level=1)
-model.load_state_dict(sd)
+model.load_state_dict(synth.make_state_dict(0))
 model = model.cuda().eval()
-video, queries = video.cuda(), queries.cuda()
+video = synth.make_video(a.frames, a.res, a.res, seed=1).cuda()
+queries = synth.make_queries(a.queries, a.frames, a.res, a.res, seed=2).cuda()
 for _ in range(a.warm + a.steps):
   out = model(video, queries)
   torch.cuda.synchronize()

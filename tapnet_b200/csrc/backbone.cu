@@ -153,37 +153,37 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __rest
   }
 }
 
-// Finalises the statistics into a per-(frame, channel) affine map y = x * scale + shift
-// (scale = w / sqrt(var + eps), shift = b - mean * scale), so the apply kernel is one FMA.
-__global__ void __launch_bounds__(256) instnorm_finalize_kernel(const double* __restrict__ sums,
-                                                                long long hw, int C, int count,
-                                                                const float* __restrict__ w,
-                                                                const float* __restrict__ b,
-                                                                float* __restrict__ mr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const int c = i % C;
-  const double mean = sums[2 * i] / (double)hw;
-  double var = sums[2 * i + 1] / (double)hw - mean * mean;
-  if (var < 0) var = 0;
-  const double scale = (double)w[c] / sqrt(var + 1e-5);
-  mr[2 * i] = (float)scale;
-  mr[2 * i + 1] = (float)((double)b[c] - mean * scale);
-}
-
 // relu(x * scale + shift) -> bf16 planes.  CTA = one frame x a chunk of pixels; a thread keeps
 // its 4 channels' (scale, shift) in registers and streams pixels, 4 independent loads in flight.
 constexpr int kApplyPixelsPerBlock = 512;
+// The statistics are finalised here, per thread, from the fp64 sums (scale = w / sqrt(var + eps),
+// shift = b - mean * scale, in fp64): one launch instead of two per norm.  `zero_next` (nullable)
+// is the OTHER statistics buffer of the ping-pong pair: the GEMM that follows accumulates into it,
+// and the first pixel block of every frame clears that frame's entries here, which replaces a
+// memset node per norm (31 fewer graph nodes per streaming frame in total).
 __global__ void __launch_bounds__(256) instnorm_relu_split_kernel(
-    const float* __restrict__ x, const float* __restrict__ mr, long long hw, int C,
-    __nv_bfloat16* __restrict__ out, long long plane_stride, int planes, int pixels_per_block) {
+    const float* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ w,
+    const float* __restrict__ b, long long hw, int C, __nv_bfloat16* __restrict__ out,
+    long long plane_stride, int planes, int pixels_per_block, double* __restrict__ zero_next,
+    int zero_count) {
   const int f = blockIdx.y;
   const int c4n = C / 4;
   const int lanes = 256 / c4n;
   const int g = threadIdx.x % c4n, pl = threadIdx.x / c4n;
-  const float4 s0 = reinterpret_cast<const float4*>(mr + ((long long)f * C + 4 * g) * 2)[0];
-  const float4 s1 = reinterpret_cast<const float4*>(mr + ((long long)f * C + 4 * g) * 2)[1];
-  const float sc[4] = {s0.x, s0.z, s1.x, s1.z}, sh[4] = {s0.y, s0.w, s1.y, s1.w};
+  float sc[4], sh[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = 4 * g + e;
+    const long long i = (long long)f * C + c;
+    const double mean = sums[2 * i] / (double)hw;
+    double var = sums[2 * i + 1] / (double)hw - mean * mean;
+    if (var < 0) var = 0;
+    const double scale = (double)w[c] / sqrt(var + 1e-5);
+    sc[e] = (float)scale;
+    sh[e] = (float)((double)b[c] - mean * scale);
+  }
+  if (zero_next != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < 2 * zero_count; i += 256) zero_next[(long long)f * 2 * zero_count + i] = 0.0;
   const long long p0 = (long long)blockIdx.x * pixels_per_block;
   long long p1 = p0 + pixels_per_block;
   if (p1 > hw) p1 = hw;
@@ -397,36 +397,21 @@ int stem_conv(const void* video, int video_u8, const float* w_packed, int frames
   return kOk;
 }
 
-int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, const float* w,
-                   const float* b, float* mr, cudaStream_t s) {
+int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, cudaStream_t s) {
   TAPIR_CHECK_ARG(C == 64 || C == 128 || C == 256, "instnorm_stats: C=%d unsupported", C);
   ProfileScope ps("backbone.instnorm_stats", s, 0.0, (double)frames * hw * C * 4);
   TAPIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * frames * C, s));
+  // single frames (streaming): keep every SM busy
   dim3 grid((unsigned)ceil_div_ll(hw, kStatPixelsPerBlock), frames);
   instnorm_stats_kernel<<<grid, 256, 0, s>>>(x, hw, C, sums);
   count_launch();
   TAPIR_LAUNCH_CHECK("instnorm_stats_kernel");
-  instnorm_finalize_kernel<<<ceil_div(frames * C, 256), 256, 0, s>>>(sums, hw, C, frames * C, w, b, mr);
-  count_launch();
-  TAPIR_LAUNCH_CHECK("instnorm_finalize_kernel");
   return kOk;
 }
 
-int instnorm_zero(int frames, int C, double* sums, cudaStream_t s) {
-  TAPIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * frames * C, s));
-  return kOk;
-}
-
-int instnorm_finalize(int frames, long long hw, int C, const double* sums, const float* w,
-                      const float* b, float* mr, cudaStream_t s) {
-  instnorm_finalize_kernel<<<ceil_div(frames * C, 256), 256, 0, s>>>(sums, hw, C, frames * C, w, b, mr);
-  count_launch();
-  TAPIR_LAUNCH_CHECK("instnorm_finalize_kernel");
-  return kOk;
-}
-
-int instnorm_relu_split(const float* x, const float* mr, int frames, long long hw, int C,
-                        __nv_bfloat16* out, long long plane_stride, int planes, cudaStream_t s) {
+int instnorm_relu_split(const float* x, const double* sums, const float* w, const float* b,
+                        int frames, long long hw, int C, __nv_bfloat16* out, long long plane_stride,
+                        int planes, double* zero_next, int zero_channels, cudaStream_t s) {
   const long long total4 = (long long)frames * hw * C / 4;
   ProfileScope ps("backbone.instnorm_apply", s, 0.0, (double)total4 * (16 + 8 * planes));
   // single frames (streaming): 512-pixel blocks would give 32 CTAs of 8 dependent load rounds
@@ -435,7 +420,8 @@ int instnorm_relu_split(const float* x, const float* mr, int frames, long long h
   const int min_ppb = 4 * (256 / (C / 4));
   while (ppb > min_ppb && ceil_div_ll(hw, ppb) * frames < 2ll * num_sms()) ppb /= 2;
   dim3 grid((unsigned)ceil_div_ll(hw, ppb), frames);
-  instnorm_relu_split_kernel<<<grid, 256, 0, s>>>(x, mr, hw, C, out, plane_stride, planes, ppb);
+  instnorm_relu_split_kernel<<<grid, 256, 0, s>>>(x, sums, w, b, hw, C, out, plane_stride, planes, ppb,
+                                                  zero_next, zero_channels);
   count_launch();
   TAPIR_LAUNCH_CHECK("instnorm_relu_split_kernel");
   return kOk;
@@ -508,8 +494,8 @@ struct BackbonePlan {
   float* buf[4];            // fp32 activation buffers (ping-pong / shortcut / conv_0 output)
   __nv_bfloat16* act;       // normalised activation planes
   __nv_bfloat16* col;       // im2col planes (stride-2 layers) / ExtraConvs hidden planes
-  double* sums;             // instance-norm statistics (fp64 sum, sum of squares)
-  float* mr;                // finalised (scale, shift) per (frame, channel)
+  double* sums[2];          // instance-norm statistics (fp64 sum, sum of squares), ping-pong:
+                            // a norm reads one while the next GEMM's epilogue fills the other
   float* splitk;            // split-K scratch for single-frame (streaming) calls
   long long act_plane, col_plane;
 };
@@ -526,8 +512,8 @@ size_t plan_backbone(Arena& a, int frames, int H, int W, int extra, int planes, 
   if (extra && hid > col_elems) col_elems = hid;
   bp->col_plane = col_elems;
   bp->col = a.take<__nv_bfloat16>(col_elems * planes);
-  bp->sums = a.take<double>((size_t)frames * 256 * 2);
-  bp->mr = a.take<float>((size_t)frames * 256 * 2);
+  bp->sums[0] = a.take<double>((size_t)frames * 256 * 2);
+  bp->sums[1] = a.take<double>((size_t)frames * 256 * 2);
   bp->splitk = a.take<float>(kBackboneSplitKBytes / sizeof(float));
   return a.off;
 }
@@ -594,8 +580,11 @@ int backbone_forward(const tapir_backbone_weights* w, const void* video, int vid
   if (video != nullptr) TAPIR_RETURN_IF(stem_conv(video, video_u8, w->stem_w, frames, H, W, x, s));
   int xi = 0;  // index of the buffer holding x
   // InstanceNorm statistics are accumulated by the epilogue of the GEMM that produces the
-  // tensor (fp64 atomics into bp.sums); only the stem output needs the stand-alone pass.
+  // tensor (fp64 atomics into bp.sums[.]); only the stem output needs the stand-alone pass.  The
+  // two statistics buffers alternate: the norm kernel that reads one clears the other for the
+  // GEMM that follows it.  sums[cur] = statistics of x.
   bool x_stats_ready = false;
+  const int cur = 0;
   for (int bi = 0; bi < TAPIR_NUM_RESNET_BLOCKS; ++bi) {
     const tapir_resnet_block& b = w->blocks[bi];
     const long long m_in = (long long)frames * h * wd;
@@ -605,12 +594,10 @@ int backbone_forward(const tapir_backbone_weights* w, const void* video, int vid
     float* shortcut_buf = bp.buf[(xi + 2) & 3];
     float* hbuf = bp.buf[(xi + 3) & 3];
     // bn_0 + relu -> planes
-    if (x_stats_ready) {
-      TAPIR_RETURN_IF(instnorm_finalize(frames, (long long)h * wd, b.cin, bp.sums, b.bn0_w, b.bn0_b, bp.mr, s));
-    } else {
-      TAPIR_RETURN_IF(instnorm_stats(x, frames, (long long)h * wd, b.cin, bp.sums, b.bn0_w, b.bn0_b, bp.mr, s));
-    }
-    TAPIR_RETURN_IF(instnorm_relu_split(x, bp.mr, frames, (long long)h * wd, b.cin, bp.act, bp.act_plane, P, s));
+    if (!x_stats_ready) TAPIR_RETURN_IF(instnorm_stats(x, frames, (long long)h * wd, b.cin, bp.sums[cur], s));
+    const bool fuse = (b.stride == 1) || (((long long)oh * ow) % 128 == 0);
+    TAPIR_RETURN_IF(instnorm_relu_split(x, bp.sums[cur], b.bn0_w, b.bn0_b, frames, (long long)h * wd, b.cin,
+                                        bp.act, bp.act_plane, P, fuse ? bp.sums[cur ^ 1] : nullptr, b.cout, s));
     const float* shortcut = x;
     if (b.has_proj) {
       GemmArgs g = linear_args(b.proj);
@@ -641,20 +628,17 @@ int backbone_forward(const tapir_backbone_weights* w, const void* video, int vid
         TAPIR_RETURN_IF(im2col_s2(bp.act, bp.act_plane, frames, h, wd, b.cin, 9, bp.col, bp.col_plane, P, s));
         g.a = bp.col; g.lda = 9 * b.cin; g.a_plane_stride = bp.col_plane;
       }
-      const bool fuse = (b.stride == 1) || (((long long)oh * ow) % 128 == 0);
       if (fuse) {
-        TAPIR_RETURN_IF(instnorm_zero(frames, b.cout, bp.sums, s));
-        g.stats = bp.sums;
+        g.stats = bp.sums[cur ^ 1];  // cleared by the bn_0 norm kernel above
         g.rows_per_frame = oh * ow;
       }
       TAPIR_RETURN_IF(gemm(g, s));
-      if (fuse) {
-        TAPIR_RETURN_IF(instnorm_finalize(frames, (long long)oh * ow, b.cout, bp.sums, b.bn1_w, b.bn1_b, bp.mr, s));
-      } else {
-        TAPIR_RETURN_IF(instnorm_stats(hbuf, frames, (long long)oh * ow, b.cout, bp.sums, b.bn1_w, b.bn1_b, bp.mr, s));
-      }
+      if (!fuse) TAPIR_RETURN_IF(instnorm_stats(hbuf, frames, (long long)oh * ow, b.cout, bp.sums[cur ^ 1], s));
     }
-    TAPIR_RETURN_IF(instnorm_relu_split(hbuf, bp.mr, frames, (long long)oh * ow, b.cout, bp.act, bp.act_plane, P, s));
+    const bool next_stats = (bi + 1 < TAPIR_NUM_RESNET_BLOCKS);  // statistics for the next block's bn_0
+    TAPIR_RETURN_IF(instnorm_relu_split(hbuf, bp.sums[cur ^ 1], b.bn1_w, b.bn1_b, frames, (long long)oh * ow,
+                                        b.cout, bp.act, bp.act_plane, P, next_stats ? bp.sums[cur] : nullptr,
+                                        b.cout, s));
     {
       GemmArgs g = linear_args(b.conv1);
       g.tag = "backbone.conv";
@@ -664,11 +648,8 @@ int backbone_forward(const tapir_backbone_weights* w, const void* video, int vid
       g.frames = frames; g.H = oh; g.W = ow; g.C = b.cout;
       g.residual = shortcut; g.ldr = b.cout;
       g.out_f32 = xnew; g.ldo = b.cout;
-      x_stats_ready = (bi + 1 < TAPIR_NUM_RESNET_BLOCKS);
-      if (x_stats_ready) {  // statistics for the next block's bn_0
-        TAPIR_RETURN_IF(instnorm_zero(frames, b.cout, bp.sums, s));
-        g.stats = bp.sums;
-      }
+      x_stats_ready = next_stats;
+      if (next_stats) g.stats = bp.sums[cur];  // cleared by the bn_1 norm kernel above
       TAPIR_RETURN_IF(gemm(g, s));
     }
     x = xnew;

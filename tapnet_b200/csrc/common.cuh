@@ -110,6 +110,19 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return __fdividef(x, 1.0f + e);
 }
 
+// Two tanh-GELUs at once on packed fp32 (mul/fma.rn.f32x2: one issue slot per pair); the two
+// ex2 and the two reciprocals stay scalar MUFU operations.  Same formula as gelu_tanh.
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+  const float2 A = make_float2(-2.3022081983f, -2.3022081983f);
+  const float2 B = make_float2(-0.1029432396f, -0.1029432396f);
+  const float2 u = __fmul2_rn(x, __ffma2_rn(__fmul2_rn(x, x), B, A));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(u.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(u.y));
+  const float2 d = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+  return make_float2(__fdividef(x.x, d.x), __fdividef(x.y, d.y));
+}
+
 // One step of the bf16 split for two values at once: returns bf16x2(a, b) (a in the low half)
 // and replaces a, b by their residuals.  Uses the packed convert (F2FP, full rate) instead of
 // two scalar F2F conversions (quarter-rate unit, scoreboard latency).

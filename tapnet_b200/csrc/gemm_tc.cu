@@ -67,6 +67,11 @@ struct TcParams {
   long long split_stride;  // elements between partial buffers (M * ldo)
   int* err;
   int debug_mode;       // bring-up only: 1 = epilogue skips TMEM loads and stores
+  // 2-SM kernel, tail of the persistent schedule: the last `tiles - tail_first` tiles are cut
+  // along N into `tail_k` pieces of 32-column chunks (piece j gets tail_base + (j < tail_extra)
+  // chunks) so that the partial last round spreads over all clusters instead of a few.
+  CUtensorMap tmB16;    // B with a 16-row box: pieces load their half-width in 16-row slabs
+  int tail_first, tail_k, tail_base, tail_extra;
 };
 
 template <int BLOCK_N, int P>
@@ -528,17 +533,33 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   }
   ptx::tc_fence_before();
   ptx::cluster_sync();
+  __syncthreads();  // redundant after the cluster barrier; lets compute-sanitizer racecheck see the
+                    // ordering between tcgen05.alloc's write of tmem_slot and the reads below
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int nkb = p.num_k_blocks;
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_work = ((p.num_m_tiles + 1) / 2) * n_tiles;
+  const int num_tiles = ((p.num_m_tiles + 1) / 2) * n_tiles;
+  const int num_work = p.tail_first + (num_tiles - p.tail_first) * p.tail_k;
   const int work_first = (int)(blockIdx.x >> 1), work_stride = (int)(gridDim.x >> 1);
-  auto decode = [&](int w, int& m_tile, int& n0) {
-    const int mm = w / n_tiles;
+  // work item -> (row pair tile, first column, width).  Full tiles first, then the tail pieces.
+  // The K-summation order of an output element does not depend on the piece it falls into, so the
+  // result is bit-identical with and without the tail split.
+  auto decode = [&](int w, int& m_tile, int& n0, int& width) {
+    int tile = w, c0 = 0;
+    width = BN;
+    if (w >= p.tail_first) {
+      const int pw = w - p.tail_first;
+      const int t = pw / p.tail_k, part = pw - t * p.tail_k;
+      tile = p.tail_first + t;
+      c0 = part * p.tail_base + (part < p.tail_extra ? part : p.tail_extra);
+      width = 32 * (p.tail_base + (part < p.tail_extra ? 1 : 0));
+    }
+    const int mm = tile / n_tiles;
     m_tile = 2 * mm + rank;
-    n0 = (w - mm * n_tiles) * BN;
+    n0 = (tile - mm * n_tiles) * BN + c0 * 32;
+    if (n0 >= p.N) width = 0;  // piece entirely right of the matrix: every role skips it
   };
 
   if (warp == kProducerWarp && lane == 0) {
@@ -546,8 +567,9 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
     int stage = 0;
     uint32_t phase = 0;
     for (int w = work_first; w < num_work; w += work_stride) {
-      int m_tile, n0;
-      decode(w, m_tile, n0);
+      int m_tile, n0, width;
+      decode(w, m_tile, n0, width);
+      if (width == 0) continue;
       int frame = 0, y0 = 0, x0 = 0;
       if (p.mode == kGemmConv3x3) {
         const int per_frame = p.tiles_x * p.tiles_y;
@@ -556,9 +578,11 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
         y0 = (r / p.tiles_x) * p.tileH;
         x0 = (r % p.tiles_x) * p.tileW;
       }
+      const int half = width / 2;  // B rows this CTA loads (each row = one 128-byte swizzle row)
+      const uint32_t stage_tx = 2u * P * (uint32_t)(Cfg::kABytes + half * kBlockK * 2);
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 201);
-        if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+        if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + P * Cfg::kABytes;
         if (p.mode == kGemmConv3x3) {
@@ -575,22 +599,34 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
             ptx::tma_load_3d_2sm(sa + pl * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * kBlockK,
                                  m_tile * kBlockM, pl);
         }
+        if (width == BN) {
 #pragma unroll
-        for (int pl = 0; pl < P; ++pl)
-          ptx::tma_load_3d_2sm(sb + pl * Cfg::kBhBytes, &p.tmBh, &full_bar[stage], kb * kBlockK,
-                               n0 + rank * (BN / 2), pl);
+          for (int pl = 0; pl < P; ++pl)
+            ptx::tma_load_3d_2sm(sb + pl * Cfg::kBhBytes, &p.tmBh, &full_bar[stage], kb * kBlockK,
+                                 n0 + rank * (BN / 2), pl);
+        } else {  // tail piece: this CTA's half of the piece in 16-row slabs (2 KB each)
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl)
+            for (int r16 = 0; r16 < half; r16 += 16)
+              ptx::tma_load_3d_2sm(sb + pl * Cfg::kBhBytes + r16 * (kBlockK * 2), &p.tmB16, &full_bar[stage],
+                                   kb * kBlockK, n0 + rank * half + r16, pl);
+        }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == kMmaWarp && lane == 0 && leader) {
     // ------------------------------------------------------------------ MMA issuer (leader only)
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * kBlockM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int w = work_first; w < num_work; w += work_stride, ++it) {
+    for (int w = work_first; w < num_work; w += work_stride) {
+      int m_tile_unused, n0_unused, width;
+      decode(w, m_tile_unused, n0_unused, width);
+      if (width == 0) continue;
+      const uint32_t idesc = ptx::make_idesc_bf16(2 * kBlockM, width);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      ++it;
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, p.err, 202);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -622,14 +658,16 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
     // ------------------------------------------------------------------ epilogue (each CTA)
     constexpr int kChunks = Cfg::kChunks;
     const int q = warp & 3;
-    const int cbase = (warp >> 2) * kChunks;
+    const int cg = warp >> 2;  // column group: 32-column chunks cg, cg + 4, cg + 8, ...
     float* bias_w = bias_smem + warp * (kChunks * 32);
     int it = 0;
-    for (int w = work_first; w < num_work; w += work_stride, ++it) {
+    for (int w = work_first; w < num_work; w += work_stride) {
+      int m_tile, n0, width;
+      decode(w, m_tile, n0, width);
+      if (width == 0) continue;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      int m_tile, n0;
-      decode(w, m_tile, n0);
+      ++it;
       const bool tile_valid = m_tile < p.num_m_tiles;
       const int r = q * 32 + lane;
       long long row;
@@ -648,26 +686,26 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
         row_ok = row < p.M;
         if (p.stats != nullptr) frame = (int)(((long long)m_tile * kBlockM) / p.rows_per_frame);
       }
-      const int colbase = n0 + cbase * 32;
       if (p.bias != nullptr) {
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < kChunks; ++j) {
-          const int c = colbase + j * 32 + lane;
+          const int c = n0 + (cg + 4 * j) * 32 + lane;
           bias_w[j * 32 + lane] = (c < p.N) ? __ldg(p.bias + c) : 0.f;
         }
         __syncwarp();
       }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 204);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cbase * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (tile_valid && p.debug_mode != 1) {
 #pragma unroll 1
         for (int i = 0; i < kChunks; ++i) {
-          const int col0 = colbase + i * 32;
-          if (col0 >= p.N) break;  // warp-uniform
+          const int chunk = cg + 4 * i;
+          const int col0 = n0 + chunk * 32;
+          if (chunk * 32 >= width || col0 >= p.N) break;  // warp-uniform
           uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + i * 32, v);
+          ptx::tmem_ld_32x32(taddr + chunk * 32, v);
           ptx::tmem_ld_wait();
           if (row_ok || p.stats != nullptr)
             store_row_chunk(p, row, col0, v, bias_w + i * 32, row_ok, frame, lane, 0);
@@ -836,7 +874,7 @@ int launch(const TcParams& p, const GemmArgs& g, cudaStream_t stream) {
     cfg.numAttrs = 1;
     TAPIR_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, P, true>, p));
   } else {
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int tiles = p.num_m_tiles * p.num_n_tiles * (p.split_k > 1 ? p.split_k : 1);  // work items
     const int grid = tiles < sms ? tiles : sms;
     gemm_tc_kernel<BLOCK_N, P, false><<<grid, num_threads(BLOCK_N), Cfg::kSmemBytes, stream>>>(p);
   }
@@ -1011,12 +1049,38 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   if (use_2sm() != 0 && g.N >= 128 && p.num_m_tiles >= 2 && (num_sms() % 2 == 0) &&
       !small_problem(p.num_m_tiles, g.N)) {
     int bn2 = use_2sm();
+    static int tail_on = -1;
+    if (tail_on < 0) { const char* e = getenv("TAPIR_B200_GEMM_TAIL"); tail_on = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
+    // Schedule cost per cluster in quarter-chunk units (a full 32-column chunk = 4): full rounds +
+    // the (possibly N-split) tail.  A piece narrower than 128 columns is bound by the shared-memory
+    // reads of its A operand, not by the tensor pipe (per k-step: 4 KB of A + 16 B per column at
+    // 128 B/clk against N/2 cycles of MMA), so a piece of c chunks costs max(4c, 8 + c) - a 32-column
+    // piece costs more than half a 128-column one, which is why pieces are at least 64 columns wide
+    // (measured: with 32-column pieces the ExtraConvs got 15 % slower, not faster).
+    auto tail_plan = [&](int bn, int* first, int* k_out, int* base, int* extra) {
+      const int W = ((p.num_m_tiles + 1) / 2) * ceil_div(g.N, bn);
+      const int C = W < num_sms() / 2 ? W : num_sms() / 2;
+      const int rem = W % C;
+      *first = W; *k_out = 1; *base = bn / 32; *extra = 0;
+      long long cost = (long long)(W / C) * (bn / 32) * 4;
+      if (rem > 0) {
+        int k = tail_on ? C / rem : 1;
+        if (k > bn / 64) k = bn / 64;
+        if (k >= 2 && W > C) {
+          *first = W - rem; *k_out = k; *base = (bn / 32) / k; *extra = (bn / 32) % k;
+          const int c = *base + (*extra > 0 ? 1 : 0);
+          cost += (4 * c > 8 + c) ? 4 * c : 8 + c;
+        } else {
+          cost += (bn / 32) * 4;
+        }
+      }
+      return cost;
+    };
+    int tf, tk, tb, te;
     if (bn2 != 128 && bn2 != 256) {
       // auto: the wider tile halves the operand requests but doubles the wave quantum
-      const int half = num_sms() / 2;
-      const int pr = (p.num_m_tiles + 1) / 2;
-      const long long c128 = (long long)ceil_div(pr * ceil_div(g.N, 128), half) * 128;
-      const long long c256 = (long long)ceil_div(pr * ceil_div(g.N, 256), half) * 256;
+      const long long c128 = tail_plan(128, &tf, &tk, &tb, &te);
+      const long long c256 = tail_plan(256, &tf, &tk, &tb, &te);
       bn2 = (g.N >= 256 && c256 * 9 <= c128 * 10) ? 256 : 128;
     }
     if (bn2 == 256 && g.N < 256) bn2 = 128;
@@ -1025,8 +1089,15 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     cuuint64_t str[2] = {(cuuint64_t)g.ldb * 2, (cuuint64_t)plane * 2};
     cuuint32_t boxh[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(bn2 / 2), 1};
     TAPIR_RETURN_IF(encode_bf16_map(&p.tmBh, g.b, 3, dims, str, boxh, "B/2sm"));
+    cuuint32_t box16[3] = {(cuuint32_t)kBlockK, 16, 1};
+    TAPIR_RETURN_IF(encode_bf16_map(&p.tmB16, g.b, 3, dims, str, box16, "B/16"));
     p.split_k = 1;
     p.split_stride = 0;
+    // Tail of the persistent schedule: W tiles on C clusters leave W % C tiles for
+    // a last round that keeps only a few clusters busy for a whole tile time (mixer `up` at 12288
+    // rows: 384 tiles on 74 clusters = 5 rounds + 14 tiles).  Those tiles are cut along N into k
+    // pieces of 32-column chunks with k * (W % C) <= C, so the last round costs about 1/k-th.
+    tail_plan(bn2, &p.tail_first, &p.tail_k, &p.tail_base, &p.tail_extra);
     if (bn2 == 128 && P == 1) return launch2<128, 1>(p, g, stream);
     if (bn2 == 128 && P == 2) return launch2<128, 2>(p, g, stream);
     if (bn2 == 256 && P == 1) return launch2<256, 1>(p, g, stream);

@@ -30,13 +30,10 @@ int split_planes(const float* src, long long ld_src, __nv_bfloat16* dst, long lo
                  cudaStream_t s);
 int stem_conv(const void* video, int video_u8, const float* w_packed, int frames, int H, int W,
               float* out, cudaStream_t s);
-int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, const float* w,
-                   const float* b, float* mr, cudaStream_t s);
-int instnorm_zero(int frames, int C, double* sums, cudaStream_t s);
-int instnorm_finalize(int frames, long long hw, int C, const double* sums, const float* w,
-                      const float* b, float* mr, cudaStream_t s);
-int instnorm_relu_split(const float* x, const float* mr, int frames, long long hw, int C,
-                        __nv_bfloat16* out, long long plane_stride, int planes, cudaStream_t s);
+int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums, cudaStream_t s);
+int instnorm_relu_split(const float* x, const double* sums, const float* w, const float* b,
+                        int frames, long long hw, int C, __nv_bfloat16* out, long long plane_stride,
+                        int planes, double* zero_next, int zero_channels, cudaStream_t s);
 int im2col_s2(const __nv_bfloat16* in, long long in_plane_stride, int frames, int H, int W, int C,
               int taps, __nv_bfloat16* out, long long out_plane_stride, int planes, cudaStream_t s);
 int layernorm_split(const float* x, long long rows, int C, const float* w, const float* b,

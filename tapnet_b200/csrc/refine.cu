@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(96) local_corr_kernel(const CorrParams p) {
 constexpr int kDwTileMax = 24;        // output frames per CTA (per query)
 constexpr int kDwHalo = 4;            // extra layer-normed rows a tile needs (2+2 or 4+0)
 constexpr int kDwRowBudget = 52;      // QB * (2*TT + 4) rows of 2 KB <= 104 KB (2 CTAs per SM)
+constexpr int kDwSmallQueries = 4;    // queries per CTA of the SMALL variant (context kept in registers)
 
 struct DwParams {
   const float* x;
@@ -275,8 +276,10 @@ __device__ __forceinline__ void ln512(const float4 (&v)[4], const float* __restr
   }
 }
 
-template <bool CAUSAL>
-__global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
+// SMALL = several queries per CTA (short clips / streaming): one CTA per SM, 128 registers, and
+// the causal hidden-state context of the next query is prefetched into registers.
+template <bool CAUSAL, bool SMALL>
+__global__ void __launch_bounds__(512, SMALL ? 1 : 2) mixer_dw_kernel(const DwParams p) {
   extern __shared__ float dw_smem[];
   const int TT = p.TT, QB = p.QB, T = p.T;
   const int RY = TT + kDwHalo;              // layer-normed rows per query
@@ -291,6 +294,26 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
   // smem row r of a query <-> frame lo + r: non-causal needs t0-2 .. t1+1, causal t0-4 .. t1-1
   const int lo = CAUSAL ? t0 - 4 : t0 - 2;
   const int nrow = (CAUSAL ? t1 : t1 + 2) - lo;
+
+  // Causal context of the hidden activation (frames -2, -1 of h1; only the first tile of a clip
+  // reads it).  With several queries per CTA (short clips, streaming) these were three dependent
+  // global loads per query, serialised over the queries (8 x 3 x ~0.7 us of a 23 us launch at
+  // T = 1); the SMALL variant issues all of them up front, before phase 1, so that the 16 KB per
+  // query stream in while the rows are layer-normed (the launch moves 46 MB of context at 1024
+  // points: it is bandwidth bound once the loads overlap).
+  const bool has_ctx2 = CAUSAL && p.ctx2_in != nullptr && t0 == 0;
+  float4 ctx_all[SMALL ? kDwSmallQueries : 1][2];
+  if (SMALL) {
+#pragma unroll
+    for (int q = 0; q < kDwSmallQueries; ++q) {
+      ctx_all[q][0] = ctx_all[q][1] = make_float4(0, 0, 0, 0);
+      if (has_ctx2 && q < nq) {
+        const float* src = p.ctx2_in + ((long long)(n0 + q) * 2) * 2048 + 4 * c;
+        ctx_all[q][0] = *reinterpret_cast<const float4*>(src);
+        ctx_all[q][1] = *reinterpret_cast<const float4*>(src + 2048);
+      }
+    }
+  }
 
   // ---- phase 1: y = LN(x) * w for every needed row (one warp per row)
   for (int rq = warp; rq < nq * nrow; rq += 16) {
@@ -322,39 +345,26 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
   }
   __syncthreads();
 
-  // ---- phase 2: thread = channel c; both depthwise convs + GELU + group sum + skip
-  float w1[4][3], w2[4][3], b1[4], b2[4];
+  // ---- phase 2: thread = channel c; both depthwise convs + GELU + group sum + skip.
+  // The four channel multipliers are handled as two packed fp32 pairs (fma.rn.f32x2 = FFMA2 on
+  // sm_100: two IEEE FMAs per issue slot, same results as scalar fmaf): 26 packed + 4 scalar
+  // FP32-pipe instructions per channel and frame instead of ~45, plus the 8 MUFU (ex2, rcp).
+  float2 w1p[2][3], w2p[2][3], b1p[2], b2p[2];  // [pair (m0,m1) / (m2,m3)][tap]
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    b1[j] = p.b1[4 * c + j];
-    b2[j] = p.b2[4 * c + j];
+  for (int h = 0; h < 2; ++h) {
+    b1p[h] = make_float2(p.b1[4 * c + 2 * h], p.b1[4 * c + 2 * h + 1]);
+    b2p[h] = make_float2(p.b2[4 * c + 2 * h], p.b2[4 * c + 2 * h + 1]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      w1[j][k] = p.w1[(4 * c + j) * 3 + k];
-      w2[j][k] = p.w2[(4 * c + j) * 3 + k];
+      w1p[h][k] = make_float2(p.w1[(4 * c + 2 * h) * 3 + k], p.w1[(4 * c + 2 * h + 1) * 3 + k]);
+      w2p[h][k] = make_float2(p.w2[(4 * c + 2 * h) * 3 + k], p.w2[(4 * c + 2 * h + 1) * 3 + k]);
     }
   }
   // h1 of frame f = first + j is a function of smem rows j, j+1, j+2 (both modes)
   const int first = CAUSAL ? t0 - 2 : t0 - 1;
-  // Causal context of the hidden activation (frames -2, -1 of h1; only the first tile of a clip
-  // reads it).  The values of query q + 1 are fetched while query q is computed: with several
-  // queries per CTA (short clips, streaming) three dependent global loads per query used to
-  // serialise - 8 queries x 3 x ~0.7 us was most of the 23 us a T = 1 launch took.
-  const bool has_ctx2 = CAUSAL && p.ctx2_in != nullptr && t0 == 0;
-  float4 ctx_next[2] = {make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
-  auto fetch_ctx2 = [&](int q) {
-    if (has_ctx2 && q < nq) {
-      const float* src = p.ctx2_in + ((long long)(n0 + q) * 2) * 2048 + 4 * c;
-      ctx_next[0] = *reinterpret_cast<const float4*>(src);
-      ctx_next[1] = *reinterpret_cast<const float4*>(src + 2048);
-    }
-  };
-  fetch_ctx2(0);
-  for (int q = 0; q < nq; ++q) {
+  auto per_query = [&](const int q, const float4 (&ctx_cur)[2]) {
     const int n = n0 + q;
     float* yq = ybuf + q * RY * 512 + c;
-    const float4 ctx_cur[2] = {ctx_next[0], ctx_next[1]};
-    fetch_ctx2(q + 1);
     if (CAUSAL && p.ctx1_out != nullptr) {
       // new context of the layer-normed input: last two frames of [ctx | y] (nets.py:153);
       // written before the rows are recycled for z
@@ -366,40 +376,47 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
       if (T == 1 && t0 == 0) p.ctx1_out[((long long)n * 2) * 512 + c] = yq[3 * 512];
     }
     float y0 = yq[0], y1 = yq[512];
-    float ha[4], hb[4], hc[4];
-    // h1 of frame f = first + j.  CHECKED handles sequence ends (zero padding / causal context /
-    // context output); the unchecked form is the same arithmetic without the tests, so a frame
-    // gives the same bits whichever form computes it (chunk invariance stays exact).
-    auto h1_math = [&](float y2, float (&o)[4]) {
+    float2 ha[2], hb[2], hc[2];  // h1 of three consecutive frames, [pair]
+    // h1 of frame f = first + j.  The tested form handles sequence ends (zero padding / causal
+    // context / context output); the untested form is the same arithmetic without the tests, so a
+    // frame gives the same bits whichever form computes it (chunk invariance stays exact).
+    auto h1_math = [&](float y2, float2 (&o)[2]) {
+      const float2 Y0 = make_float2(y0, y0), Y1 = make_float2(y1, y1), Y2 = make_float2(y2, y2);
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
-        o[m] = gelu_tanh(fmaf(w1[m][2], y2, fmaf(w1[m][1], y1, fmaf(w1[m][0], y0, b1[m]))));
+      for (int h = 0; h < 2; ++h) {
+        const float2 a = __ffma2_rn(w1p[h][2], Y2, __ffma2_rn(w1p[h][1], Y1, __ffma2_rn(w1p[h][0], Y0, b1p[h])));
+        o[h] = gelu_tanh2(a);
+      }
     };
-    auto h1 = [&](int j, float (&o)[4]) {
+    auto h1 = [&](int j, float2 (&o)[2]) {
       const int f = first + j;
       const float y2 = yq[(j + 2) * 512];
       if (f >= 0 && f < T) {
         h1_math(y2, o);
         if (CAUSAL && p.ctx2_out != nullptr && f >= T - 2)  // last two frames of [ctx | h1] (nets.py:167)
           *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2 + (f - (T - 2))) * 2048 + 4 * c) =
-              make_float4(o[0], o[1], o[2], o[3]);
+              make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
       } else if (has_ctx2 && f >= -2 && f < 0) {
-        const float4 v = (f == -2) ? ctx_cur[0] : ctx_cur[1];
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        const float4 v = SMALL ? ((f == -2) ? ctx_cur[0] : ctx_cur[1])
+                               : *reinterpret_cast<const float4*>(p.ctx2_in + ((long long)n * 2 + (f + 2)) * 2048 + 4 * c);
+        o[0] = make_float2(v.x, v.y);
+        o[1] = make_float2(v.z, v.w);
       } else {
-        o[0] = o[1] = o[2] = o[3] = 0.f;  // zero padding of the second conv's input
+        o[0] = o[1] = make_float2(0.f, 0.f);  // zero padding of the second conv's input
       }
       y0 = y1;
       y1 = y2;
     };
     // second conv + group sum + skip for output frame i, from h1 of frames i-1, i, i+1 (a, b, c);
-    // rows <= i + 2 of this column are dead by then: z[t0 + i] is parked in row i
-    auto emit = [&](float* yrow, const float* xrow, float* zrow, const float (&a)[4],
-                    const float (&b)[4], const float (&cc)[4]) {
-      float acc = *xrow;
+    // rows <= i + 2 of this column are dead by then: z[t0 + i] is parked in row i.  Summation
+    // order of the reference (nets.py:178-180): ((m0 + m1) + m2) + m3, then + skip.
+    auto emit = [&](float* yrow, const float* xrow, float* zrow, const float2 (&a)[2],
+                    const float2 (&b)[2], const float2 (&cc)[2]) {
+      float2 t[2];
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
-        acc += fmaf(w2[m][2], cc[m], fmaf(w2[m][1], b[m], fmaf(w2[m][0], a[m], b2[m])));
+      for (int h = 0; h < 2; ++h)
+        t[h] = __ffma2_rn(w2p[h][2], cc[h], __ffma2_rn(w2p[h][1], b[h], __ffma2_rn(w2p[h][0], a[h], b2p[h])));
+      const float acc = (((t[0].x + t[0].y) + t[1].x) + t[1].y) + *xrow;
       *yrow = acc;
       *zrow = acc;
     };
@@ -409,7 +426,7 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
     // context.  Written only now, after both old slots were read (in/out buffers may alias).
     if (CAUSAL && p.ctx2_out != nullptr && T == 1 && t0 == 0)
       *reinterpret_cast<float4*>(p.ctx2_out + ((long long)n * 2) * 2048 + 4 * c) =
-          make_float4(hb[0], hb[1], hb[2], hb[3]);
+          make_float4(hb[0].x, hb[0].y, hb[1].x, hb[1].y);
     const int nout = t1 - t0;
     // output frames whose newest h1 frame (first + i + 2) needs no end-of-sequence handling
     int i_lo = max(0, -(first + 2));
@@ -424,7 +441,7 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
         h1(i + 2, hc);
         emit(yp, xp, zp, ha, hb, hc);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) { ha[m] = hb[m]; hb[m] = hc[m]; }
+        for (int h = 0; h < 2; ++h) { ha[h] = hb[h]; hb[h] = hc[h]; }
       }
     };
     checked_until(i_lo);
@@ -443,6 +460,14 @@ __global__ void __launch_bounds__(512, 2) mixer_dw_kernel(const DwParams p) {
       emit(yp + 1024, xp + 1024, zp + 1024, hc, ha, hb);
     }
     checked_until(nout);
+  };
+  if constexpr (SMALL) {
+    // unrolled so that each copy indexes ctx_all with a constant (it must stay in registers)
+#pragma unroll
+    for (int q = 0; q < kDwSmallQueries; ++q)
+      if (q < nq) per_query(q, ctx_all[q]);
+  } else {
+    for (int q = 0; q < nq; ++q) per_query(q, ctx_all[0]);
   }
   __syncthreads();
 
@@ -616,8 +641,10 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
   static PerDeviceOnce configured;
   if (configured.pending()) {
     const int max_smem = kDwRowBudget * 512 * (int)sizeof(float);
-    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    TAPIR_CUDA(cudaFuncSetAttribute(mixer_dw_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured.mark();
   }
   {  // nets.py:235 linear
@@ -640,9 +667,10 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     d.TT = T < kDwTileMax ? T : kDwTileMax;
     d.QB = kDwRowBudget / (2 * d.TT + kDwHalo);
     if (d.QB < 1) d.QB = 1;
-    if (d.QB > 8) d.QB = 8;
+    if (d.QB > kDwSmallQueries) d.QB = kDwSmallQueries;
     // few rows in total (streaming): fewer queries per CTA so that every SM gets one
-    while (d.QB > 1 && (long long)ceil_div(n, d.QB) * ceil_div(T, d.TT) < 2ll * num_sms()) d.QB /= 2;
+    // (the several-queries-per-CTA variant runs one CTA per SM)
+    while (d.QB > 2 && (long long)ceil_div(n, d.QB) * ceil_div(T, d.TT) < (long long)num_sms()) d.QB /= 2;
     if (d.QB > n) d.QB = n;
     d.ln_w = blk.ln_w; d.w1 = blk.dw1_w; d.b1 = blk.dw1_b; d.w2 = blk.dw2_w; d.b2 = blk.dw2_b;
     d.ln1_w = blk.ln1_w;
@@ -654,10 +682,13 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     const int dw_smem = d.QB * (2 * d.TT + kDwHalo) * 512 * (int)sizeof(float);
     {
       ProfileScope ps("mixer.dw", s, (double)rows * 2048 * 12, (double)rows * 512 * (8 + 2 * P));
+      const bool small = d.QB > 1;
       if (io->causal) {
-        mixer_dw_kernel<true><<<grid, 512, dw_smem, s>>>(d);
+        if (small) mixer_dw_kernel<true, true><<<grid, 512, dw_smem, s>>>(d);
+        else mixer_dw_kernel<true, false><<<grid, 512, dw_smem, s>>>(d);
       } else {
-        mixer_dw_kernel<false><<<grid, 512, dw_smem, s>>>(d);
+        if (small) mixer_dw_kernel<false, true><<<grid, 512, dw_smem, s>>>(d);
+        else mixer_dw_kernel<false, false><<<grid, 512, dw_smem, s>>>(d);
       }
     }
     count_launch();

@@ -345,7 +345,51 @@ struct HeadTcSmem {
   float mean32[16][32];
   float bcast[4];
   int bcast_i;
+  // one slot per block reduction of a map (4 per map): a slot is rewritten only in the next map,
+  // at least one __syncthreads later, so every reduction needs a single barrier
+  float slot_f[4][16 * 3];
+  int slot_i[4][16];
 };
+
+// Single-barrier block reductions (16 warps): warp results go to a private slot, then EVERY thread
+// folds the 16 partials itself in the same fixed order (16 broadcast LDS instead of two more
+// barriers; the head kernel spent 21 % of its stall samples on barriers).
+template <class SM>
+__device__ __forceinline__ void block_max_first_1s(float v, int idx, SM& sm, int slot, float* out_v,
+                                                   int* out_i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sm.slot_f[slot][warp] = v; sm.slot_i[slot][warp] = idx; }
+  __syncthreads();
+  float bv = sm.slot_f[slot][0];
+  int bi = sm.slot_i[slot][0];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) {
+    const float kv = sm.slot_f[slot][k];
+    const int ki = sm.slot_i[slot][k];
+    if (kv > bv || (kv == bv && ki < bi)) { bv = kv; bi = ki; }
+  }
+  *out_v = bv;
+  *out_i = bi;
+}
+
+template <class SM>
+__device__ __forceinline__ void block_sum3_1s(float a, float b, float c, SM& sm, int slot, float* oa,
+                                              float* ob, float* oc) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sm.slot_f[slot][warp * 3] = a; sm.slot_f[slot][warp * 3 + 1] = b; sm.slot_f[slot][warp * 3 + 2] = c; }
+  __syncthreads();
+  float x = 0, y = 0, z = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { x += sm.slot_f[slot][k * 3]; y += sm.slot_f[slot][k * 3 + 1]; z += sm.slot_f[slot][k * 3 + 2]; }
+  *oa = x; *ob = y; *oc = z;
+}
 
 template <class SM>
 __device__ __forceinline__ void block_max_first(float v, int idx, SM& sm, int nwarps, float* out_v,
@@ -440,9 +484,11 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
   float2 pre = make_float2(0.f, 0.f);
   if ((int)blockIdx.x < num_maps)
     pre = reinterpret_cast<const float2*>(cost_volume + (long long)blockIdx.x * (kG * kG))[tid];
+  __syncthreads();  // phase A's zero fill of `cv` is ordered before the first map's interior writes
   for (int map = blockIdx.x; map < num_maps; map += gridDim.x) {
   const int n = map / T, t = map - n * T;
-  __syncthreads();  // previous map fully consumed (planes, stap, mean32) / phase A visible
+  // (no barrier here: `cv` was last read in the previous map's phase B, several barriers ago;
+  // the barrier below publishes the new map and, on the first trip, the staged weights)
   {
     const int i = 2 * tid;  // pixels i, i+1 of the 32x32 map (same row)
     float* d = sm.cv + ((i >> 5) + 1) * (kG + 2) + (i & 31) + 1;
@@ -533,12 +579,12 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
   }
   int dummy;
   float gmax;
-  block_max_first(fmaxf(heat[0], heat[1]), 0, sm, 16, &gmax, &dummy);
+  block_max_first_1s(fmaxf(heat[0], heat[1]), 0, sm, 0, &gmax, &dummy);
   float e[2];
   e[0] = expf(heat[0] - gmax);
   e[1] = expf(heat[1] - gmax);
   float gsum, u1, u2;
-  block_sum3(e[0] + e[1], 0.f, 0.f, sm, 16, &gsum, &u1, &u2);
+  block_sum3_1s(e[0] + e[1], 0.f, 0.f, sm, 1, &gsum, &u1, &u2);
   float prob[2];
   float pbest = -1.f;
   int ibest = 0;
@@ -549,7 +595,7 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
   }
   float pm;
   int am;
-  block_max_first(pbest, ibest, sm, 16, &pm, &am);
+  block_max_first_1s(pbest, ibest, sm, 2, &pm, &am);
   const float cx = (float)(am & 31) + 0.5f, cy = (float)(am >> 5) + 0.5f;
   float sx = 0.f, sy = 0.f, sw = 0.f;
 #pragma unroll
@@ -559,7 +605,7 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
     if (dx * dx + dy * dy < 25.f) { sx += px * prob[p]; sy += py * prob[p]; sw += prob[p]; }
   }
   float tx, ty, tw;
-  block_sum3(sx, sy, sw, sm, 16, &tx, &ty, &tw);
+  block_sum3_1s(sx, sy, sw, sm, 3, &tx, &ty, &tw);
 
   // ---- phase D: hid3 (pad(0,2,0,2), conv3x3 stride 2, 16->32) on the tensor cores.
   // warp = output row oy (16 output pixels = one m16 tile), 4 n8 tiles, one k16 step per tap.
@@ -606,36 +652,42 @@ __global__ void __launch_bounds__(kHT, 1) cost_volume_head_tc_kernel(
     }
   }
   __syncthreads();
-  if (tid < 32) {
+  // The rest of the map (channel means, 32 -> 16 -> 2 MLP, outputs) is a few hundred FLOPs: warp 0
+  // does it alone with shuffles while the other 15 warps already stage the next map (the mean32
+  // rows are rewritten only in the next map's phase D, four barriers from here).
+  if (warp == 0) {
     float m = 0.f;
-    for (int k = 0; k < 16; ++k) m += sm.mean32[k][tid];
-    sm.mean32[0][tid] = m * (1.0f / 256.0f);
-  }
-  __syncthreads();
-  if (tid < 16) {
-    float a = sm.b4[tid];
-    for (int k = 0; k < 32; ++k) a = fmaf(sm.mean32[0][k], sm.w4[tid * 32 + k], a);
-    sm.mean32[1][tid] = fmaxf(a, 0.f);
-  }
-  __syncthreads();
-  if (tid < 2) {
-    float a = sm.b5[tid];
-    for (int k = 0; k < 16; ++k) a = fmaf(sm.mean32[1][k], sm.w5[tid * 16 + k], a);
-    const long long o = (long long)n * T + t;
-    if (tid == 0) occ_out[o] = a; else expd_out[o] = a;
-  }
-  if (tid == 0) {
-    const long long o = (long long)n * T + t;
-    const float den = fmaxf(tw, 1e-12f);
-    float px = __fdiv_rn(__fmul_rn(tx / den, (float)init_w), (float)kG);
-    float py = __fdiv_rn(__fmul_rn(ty / den, (float)init_h), (float)kG);
-    if (query_tyx != nullptr) {
-      const float qf = rintf(query_tyx[n * 3 + 0]);
-      if (qf == (float)t) { px = query_tyx[n * 3 + 2]; py = query_tyx[n * 3 + 1]; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m += sm.mean32[k][lane];
+    m *= (1.0f / 256.0f);                       // lane = channel
+    float a = (lane < 16) ? sm.b4[lane] : 0.f;  // hid4: 32 -> 16, ReLU
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float mk = __shfl_sync(0xffffffffu, m, k);
+      if (lane < 16) a = fmaf(mk, sm.w4[lane * 32 + k], a);
     }
-    points[o * 2 + 0] = px;
-    points[o * 2 + 1] = py;
-    if (argmax_out != nullptr) argmax_out[o] = am;
+    a = fmaxf(a, 0.f);
+    float o2 = (lane < 2) ? sm.b5[lane] : 0.f;  // occ_out: 16 -> 2
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float hk = __shfl_sync(0xffffffffu, a, k);
+      if (lane < 2) o2 = fmaf(hk, sm.w5[lane * 16 + k], o2);
+    }
+    const long long o = (long long)n * T + t;
+    if (lane == 0) occ_out[o] = o2;
+    if (lane == 1) expd_out[o] = o2;
+    if (lane == 0) {
+      const float den = fmaxf(tw, 1e-12f);
+      float px = __fdiv_rn(__fmul_rn(tx / den, (float)init_w), (float)kG);
+      float py = __fdiv_rn(__fmul_rn(ty / den, (float)init_h), (float)kG);
+      if (query_tyx != nullptr) {
+        const float qf = rintf(query_tyx[n * 3 + 0]);
+        if (qf == (float)t) { px = query_tyx[n * 3 + 2]; py = query_tyx[n * 3 + 1]; }
+      }
+      points[o * 2 + 0] = px;
+      points[o * 2 + 1] = py;
+      if (argmax_out != nullptr) argmax_out[o] = am;
+    }
   }
   }  // map loop
 }
