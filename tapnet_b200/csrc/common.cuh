@@ -105,9 +105,10 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float A = -2.3022081983f;
   const float B = -0.1029432396f;
   const float u = x * fmaf(x * x, B, A);
-  float e;
+  float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u));
-  return __fdividef(x, 1.0f + e);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));  // 1 + e in [1, +inf]: see gelu_tanh2
+  return x * r;
 }
 
 // Two tanh-GELUs at once on packed fp32 (mul/fma.rn.f32x2: one issue slot per pair); the two
@@ -120,7 +121,12 @@ __device__ __forceinline__ float2 gelu_tanh2(float2 x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(u.x));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(u.y));
   const float2 d = __fadd2_rn(e, make_float2(1.0f, 1.0f));
-  return make_float2(__fdividef(x.x, d.x), __fdividef(x.y, d.y));
+  // d is in [1, +inf]: rcp.approx needs none of div.approx's range handling (which costs an
+  // FSETP and two FMULs per division); rcp(+inf) = 0 gives gelu(-large) = -0 like the quotient
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return __fmul2_rn(x, r);
 }
 
 // One step of the bf16 split for two values at once: returns bf16x2(a, b) (a in the low half)
