@@ -43,7 +43,7 @@ def choice(m_rows, n, planes, tail=True):
   if n >= 128 and m_tiles >= 2 and not small:
     c128, _ = _tail_plan(pr, n, 128, tail)
     c256, _ = _tail_plan(pr, n, 256, tail)
-    bn = 256 if (n >= 256 and c256 * 9 <= c128 * 10) else 128
+    bn = 256 if (n >= 256 and c256 * (10 if planes == 3 else 9) <= c128 * 10) else 128
     cost, tiles = _tail_plan(pr, n, bn, tail)
     return f'2SM 256x{bn}', tiles, SMS // 2, cost / (bn // 32 * 4)
   bn = 64 if (n <= 64 or (small and m_tiles * math.ceil(n / 128) * 2 <= SMS)) else 128

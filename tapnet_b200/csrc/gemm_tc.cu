@@ -1081,7 +1081,10 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
       // auto: the wider tile halves the operand requests but doubles the wave quantum
       const long long c128 = tail_plan(128, &tf, &tk, &tb, &te);
       const long long c256 = tail_plan(256, &tf, &tk, &tb, &te);
-      bn2 = (g.N >= 256 && c256 * 9 <= c128 * 10) ? 256 : 128;
+      // three planes (the cost volume: 6 MMAs per k-block, only two 96 KB stages fit at 256 columns,
+      // few tiles per CTA so fill / drain matter): no bias towards the wide tile
+      const long long bias = (P == 3) ? 10 : 9;
+      bn2 = (g.N >= 256 && c256 * bias <= c128 * 10) ? 256 : 128;
     }
     if (bn2 == 256 && g.N < 256) bn2 = 128;
     const long long plane = g.b_plane_stride > 0 ? g.b_plane_stride : (long long)g.N * g.ldb;
