@@ -1033,7 +1033,18 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)kBlockM, 1};
     TAPIR_RETURN_IF(encode_bf16_map(&p.tmA, g.a, 3, dims, str, box, "A"));
   }
-  const int bn = pick_block_n(p.num_m_tiles, g.N, P);
+  // Split-K (deterministic two-pass, below) for problems that cannot half-fill the GPU: on by
+  // default, TAPIR_B200_SPLITK=0 disables.  (Round 1 measured "no gain at K = 2048" with a launch
+  // that only started one CTA per TILE, so the split gave no extra parallelism; fixed in round 2.)
+  static int splitk_on = -1;
+  if (splitk_on < 0) { const char* e = getenv("TAPIR_B200_SPLITK"); splitk_on = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
+  const bool splittable = splitk_on && g.splitk_ws != nullptr && g.stats == nullptr && p.num_k_blocks >= 32;
+  int bn = pick_block_n(p.num_m_tiles, g.N, P);
+  // a small problem that will be split over K keeps 128-wide tiles: the parallelism comes from K,
+  // and wide tiles re-read the A operand half as often (these sizes are L2 -> SM traffic bound)
+  if (splittable && bn == 64 && g.N > 64 && small_problem(p.num_m_tiles, g.N) &&
+      p.num_m_tiles * ceil_div(g.N, 128) * 2 <= num_sms() && getenv("TAPIR_B200_BLOCK_N") == nullptr)
+    bn = 128;
   p.num_n_tiles = ceil_div(g.N, bn);
   {
     const long long plane = g.b_plane_stride > 0 ? g.b_plane_stride : (long long)g.N * g.ldb;
@@ -1114,14 +1125,11 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   p.split_stride = 0;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = num_sms();
-  // On by default (TAPIR_B200_SPLITK=0 disables) for K >= 4096 only: a GEMM launch has ~12 us of
-  // fixed cost, so splitting K = 2048 saves less than the reduce pass costs, but the ExtraConvs'
-  // 1024 -> 256 convolution of ONE frame is 8 row tiles x K = 9216 (56 us on 16 SMs unsplit).  The
-  // summation order then depends on the row count; only problems that cannot half-fill the GPU
-  // split, so offline clips keep their exact chunk / permutation invariance.
-  static int splitk_on = -1;
-  if (splitk_on < 0) { const char* e = getenv("TAPIR_B200_SPLITK"); splitk_on = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
-  if (splitk_on && g.splitk_ws != nullptr && g.stats == nullptr && tiles * 2 <= sms && p.num_k_blocks >= 64) {
+  // K >= 2048 only (mixer `down` at ~1000 rows, the ExtraConvs of one frame: 8 row tiles x K = 9216
+  // took 56 us on 16 SMs unsplit).  The summation order then depends on the row count; only problems
+  // that cannot half-fill the GPU split, so offline clips keep their exact chunk / permutation
+  // invariance.
+  if (splittable && tiles * 2 <= sms) {
     int S = sms / tiles;
     if (S > 8) S = 8;
     if (S > p.num_k_blocks / 4) S = p.num_k_blocks / 4;
