@@ -24,11 +24,11 @@
 extern "C" {
 #endif
 
-#define TAPIR_B200_ABI_VERSION 1
+#define TAPIR_B200_ABI_VERSION 2 /* 2: TAPIR_MAX_CORR_LEVELS 3 -> 5 (tapir_corr_args grew) */
 #define TAPIR_MAX_MIXER_BLOCKS 12
 #define TAPIR_NUM_RESNET_BLOCKS 8
 #define TAPIR_MAX_EXTRA_BLOCKS 5
-#define TAPIR_MAX_CORR_LEVELS 3
+#define TAPIR_MAX_CORR_LEVELS 5 /* hires + lowres + up to 3 pooled levels (pyramid_level <= 3) */
 
 /* A dense layer / convolution prepared for the split-bf16 tensor-core GEMM:
  * w = bf16 planes [planes][N][K] (K padded with zeros to a multiple of 64; for 3x3

@@ -31,6 +31,8 @@ CASES = {
     # constructor argument initial_resolution (tapir_model.py:86): a 24 x 40 cost-volume map
     'bootstapir_ir192x320x3_n10': (dict(pyramid_level=1, initial_resolution=(192, 320)), 3, 10, 192,
                                    320, 'offline'),
+    # constructor argument pyramid_level = 2: two pooled levels, four correlation levels (mixer in 584)
+    'tapir_pl2_256x3_n6': (dict(pyramid_level=2), 3, 6, 256, 256, 'offline'),
 }
 
 

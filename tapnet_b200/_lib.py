@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, 'libtapir_b200.so')
 MAX_MIXER_BLOCKS = 12
 NUM_RESNET_BLOCKS = 8
 MAX_EXTRA_BLOCKS = 5
-MAX_CORR_LEVELS = 3
+MAX_CORR_LEVELS = 5
 
 
 class Linear(Structure):

@@ -1038,7 +1038,12 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   // that only started one CTA per TILE, so the split gave no extra parallelism; fixed in round 2.)
   static int splitk_on = -1;
   if (splitk_on < 0) { const char* e = getenv("TAPIR_B200_SPLITK"); splitk_on = (e != nullptr && atoi(e) == 0) ? 0 : 1; }
-  const bool splittable = splitk_on && g.splitk_ws != nullptr && g.stats == nullptr && p.num_k_blocks >= 32;
+  // Only for at most 1024 rows (8 row tiles: the streaming regime).  The summation order of a
+  // split GEMM depends on the row count, and anything larger keeps the exact chunk / permutation
+  // invariance of the offline path (tests/test_properties_gpu.py re-chunks config 2 into 1776-row
+  // chunks and demands bit-identical tracks).
+  const bool splittable = splitk_on && g.splitk_ws != nullptr && g.stats == nullptr &&
+                          p.num_k_blocks >= 32 && p.num_m_tiles <= 8;
   int bn = pick_block_n(p.num_m_tiles, g.N, P);
   // a small problem that will be split over K keeps 128-wide tiles: the parallelism comes from K,
   // and wide tiles re-read the A operand half as often (these sizes are L2 -> SM traffic bound)

@@ -94,7 +94,7 @@ __device__ __forceinline__ void cell_dots(const float* __restrict__ frame, int g
   }
 }
 
-__global__ void __launch_bounds__(96) local_corr_kernel(const CorrParams p) {
+__global__ void __launch_bounds__(32 * TAPIR_MAX_CORR_LEVELS) local_corr_kernel(const CorrParams p) {
   __shared__ float table[TAPIR_MAX_CORR_LEVELS][kBoxCells];
   __shared__ float corr[TAPIR_MAX_CORR_LEVELS * 49];
   const tapir_corr_args& a = p.a;
@@ -565,7 +565,7 @@ int local_corr(const tapir_corr_args* a, cudaStream_t s) {
   // N*T*(64 cells * sum C * e + 384*4 + 8 + 147*4)
   ProfileScope ps("local_corr", s, (double)rows * (cell_bytes / 2 + 1200),
                   (double)rows * (cell_bytes + 384 * 4 + 8 + 49.0 * a->num_levels * 4));
-  local_corr_kernel<<<(unsigned)rows, 96, 0, s>>>(p);
+  local_corr_kernel<<<(unsigned)rows, 32 * a->num_levels, 0, s>>>(p);  // one warp per pyramid level
   count_launch();
   TAPIR_LAUNCH_CHECK("local_corr_kernel");
   return kOk;

@@ -146,8 +146,8 @@ class TAPIR(nn.Module):
     self.precision = precision
     self._planes = _PRECISIONS[precision]
     self._has_extra = bool(extra_convs)
-    if pyramid_level not in (0, 1):
-      raise NotImplementedError('pyramid_level must be 0 or 1 (2 or 3 correlation levels)')
+    if pyramid_level not in (0, 1, 2, 3):
+      raise NotImplementedError('pyramid_level must be 0..3 (2 to 5 correlation levels)')
 
     # Parameters: same names / shapes / order as the reference state dict.
     for key, shape in schema.state_dict_schema(pyramid_level, extra_convs).items():
@@ -640,14 +640,20 @@ class TAPIR(nn.Module):
     pooled = {}
 
     def pooled_for(level, bi):
+      """The `pyramid_level` pooled grids of a resolution level (each the 2x2 average of the one
+      before it, tapir_model.py:519-527)."""
       key = (level, bi)
       if key not in pooled:
         g = feature_grids.lowres[level][bi].contiguous()
-        t, gh, gw, c = g.shape
-        out = new(t, gh // 2, gw // 2, c)
-        _lib.check(lib.tapir_pool_pyramid(_ptr(g), t, gh, gw, c, _ptr(out), stream),
-                   'tapir_pool_pyramid')
-        pooled[key] = out
+        outs = []
+        for _ in range(self.pyramid_level):
+          t, gh, gw, c = g.shape
+          out = new(t, gh // 2, gw // 2, c)
+          _lib.check(lib.tapir_pool_pyramid(_ptr(g), t, gh, gw, c, _ptr(out), stream),
+                     'tapir_pool_pyramid')
+          outs.append(out)
+          g = out
+        pooled[key] = outs
       return pooled[key]
 
     chunk_q = max(1, min(N, _MAX_ROWS_PER_CHUNK // max(T, 1), 65535))
@@ -693,7 +699,7 @@ class TAPIR(nn.Module):
           hires_g = feature_grids.hires[level][bi].contiguous()
           lowres_g = feature_grids.lowres[level][bi].contiguous()
           ca = _lib.CorrArgs()
-          grids = [hires_g, lowres_g] + ([pooled_for(level, bi)] if self.pyramid_level else [])
+          grids = [hires_g, lowres_g] + (pooled_for(level, bi) if self.pyramid_level else [])
           for li, g in enumerate(grids):
             ca.levels[li].grid = g.data_ptr()
             ca.levels[li].h, ca.levels[li].w, ca.levels[li].C = g.shape[1], g.shape[2], g.shape[3]

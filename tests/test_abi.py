@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
   lib = _lib.load()
-  assert lib.tapir_abi_version() == 1
+  assert lib.tapir_abi_version() == 2
   assert isinstance(lib.tapir_last_error(), bytes)
 
 
@@ -50,7 +50,7 @@ def test_struct_sizes_match_header():
   assert ctypes.sizeof(_lib.MixerBlock) == 48 + 64
   assert ctypes.sizeof(_lib.MixerWeights) == 64 + 8 + 12 * 112 + 8
   assert ctypes.sizeof(_lib.MixerIO) == 8 + 8 + 16 + 32 + 8 + 8
-  assert ctypes.sizeof(_lib.CorrArgs) == 72 + 24 + 24 + 48 + 24
+  assert ctypes.sizeof(_lib.CorrArgs) == 5 * 24 + 24 + 24 + 48 + 24  # 5 correlation levels (ABI 2)
   assert ctypes.sizeof(_lib.UpdateArgs) == 8 + 40 + 48 + 7 * 8
 
 
@@ -108,7 +108,7 @@ def test_c_host_example_links_and_fails_loudly_without_a_gpu(tmp_path):
                   f'-Wl,-rpath,{libdir}', '-o', str(exe)], check=True)
   out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, timeout=120).stdout
   lines = dict(l.split(' ', 1) for l in out.strip().splitlines())
-  assert lines['abi'] == '1'
+  assert lines['abi'] == '2'
   assert int(lines['backbone_ws']) > 1 << 30 and int(lines['mixer_ws']) > 0
   assert lines['bad_args'].startswith('rc=1 ') and 'bad arguments' in lines['bad_args']
   if not torch.cuda.is_available():

@@ -39,7 +39,8 @@ def _inputs(meta):
 
 
 @pytest.mark.parametrize('name', ['c1_bootstapir_256x8_n16', 'tapir_pl0_noextra_256x4_n8',
-                                  'bootstapir_320x384x4_n12', 'causal_256x6_n16'])
+                                  'bootstapir_320x384x4_n12', 'causal_256x6_n16',
+                                  'tapir_pl2_256x3_n6'])
 def test_forward_matches_reference_golden(name):
   g = load_golden(name)
   meta = g['meta']

@@ -17,7 +17,7 @@ LOGIT_TOL = 5e-5
 
 OFFLINE = ['c1_bootstapir_256x8_n16', 'tapir_pl0_noextra_256x4_n8', 'bootstapir_320x384x4_n12',
            'causal_256x6_n16', 'causal_480x3_n8', 'bootstapir_1024x2_n6',
-           'bootstapir_ir192x320x3_n10']
+           'bootstapir_ir192x320x3_n10', 'tapir_pl2_256x3_n6']
 CAUSAL = ['causal_256x6_n16', 'causal_480x3_n8']   # the second: live-demo shape, two levels
 
 

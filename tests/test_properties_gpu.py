@@ -261,3 +261,19 @@ def test_host_clip_streamed_in_equals_device_clip():
   b = model(v480.pin_memory(), q480.pin_memory())
   assert torch.equal(a['tracks'], b['tracks'])
   U.record('host_clip_streaming', equal=1)
+
+
+def test_batch_of_two_clips_equals_two_calls():
+  """B = 2 (the reference's einshape equations carry a batch axis everywhere): same results as
+  two B = 1 calls, bit for bit."""
+  model, _, _ = get_model()
+  T, N = 5, 12
+  v = torch.cat([synth.make_video(T, seed=1), synth.make_video(T, seed=5)], 0).cuda()
+  q = torch.cat([synth.make_queries(N, T, seed=2), synth.make_queries(N, T, seed=6)], 0).cuda()
+  both = model(v, q)
+  for b in range(2):
+    one = model(v[b:b + 1], q[b:b + 1])
+    assert torch.equal(both['tracks'][b], one['tracks'][0])
+    assert torch.equal(both['occlusion'][b], one['occlusion'][0])
+    assert torch.equal(both['expected_dist'][b], one['expected_dist'][0])
+  U.record('batch_two_clips', equal=1)

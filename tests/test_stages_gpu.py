@@ -34,7 +34,7 @@ def maxerr(a, b):
 
 def test_abi_loads():
   lib = _lib.load()
-  assert lib.tapir_abi_version() == 1
+  assert lib.tapir_abi_version() == 2
 
 
 @pytest.mark.parametrize('shape', [(2, 256, 256), (1, 64, 96)])
