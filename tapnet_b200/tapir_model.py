@@ -479,7 +479,10 @@ class TAPIR(nn.Module):
           c = min(chunk, nf - s0)
           last = s0 + c >= nf
           if streamed:
-            sub = max(1, -(-c // _H2D_SUBCHUNKS))
+            # sub-chunks of >= ~4 MB (each costs ~70 us of host time: copy, event, stem launch),
+            # at most _H2D_SUBCHUNKS per pass
+            nsub = max(1, min(_H2D_SUBCHUNKS, (c * h * w * 3 * flat_src.element_size()) >> 22))
+            sub = max(1, -(-c // nsub))
             for a in range(s0, s0 + c, sub):
               b = min(a + sub, s0 + c)
               with torch.cuda.stream(cs):
