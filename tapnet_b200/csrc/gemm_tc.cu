@@ -1099,7 +1099,9 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
       const long long c256 = tail_plan(256, &tf, &tk, &tb, &te);
       // three planes (the cost volume: 6 MMAs per k-block, only two 96 KB stages fit at 256 columns,
       // few tiles per CTA so fill / drain matter): no bias towards the wide tile
-      const long long bias = (P == 3) ? 10 : 9;
+      static int bias_env = -1;  // bring-up A/B of the tile-width policy (TAPIR_B200_GEMM_BIAS=9|10)
+      if (bias_env < 0) { const char* e = getenv("TAPIR_B200_GEMM_BIAS"); bias_env = e != nullptr ? atoi(e) : 0; }
+      const long long bias = bias_env > 0 ? bias_env : ((P == 3) ? 10 : 9);
       bn2 = (g.N >= 256 && c256 * bias <= c128 * 10) ? 256 : 128;
     }
     if (bn2 == 256 && g.N < 256) bn2 = 128;

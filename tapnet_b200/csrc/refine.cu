@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(32 * TAPIR_MAX_CORR_LEVELS) local_corr_kernel(
 constexpr int kDwTileMax = 24;        // output frames per CTA (per query)
 constexpr int kDwHalo = 4;            // extra layer-normed rows a tile needs (2+2 or 4+0)
 constexpr int kDwRowBudget = 52;      // QB * (2*TT + 4) rows of 2 KB <= 104 KB (2 CTAs per SM)
-constexpr int kDwSmallQueries = 4;    // queries per CTA of the SMALL variant (context kept in registers)
+constexpr int kDwSmallQueries = 8;    // max queries per CTA of the SMALL variant
+constexpr int kDwCtxWindow = 4;       // of which this many have their hidden-state context in registers
 
 struct DwParams {
   const float* x;
@@ -302,17 +303,20 @@ __global__ void __launch_bounds__(512, SMALL ? 1 : 2) mixer_dw_kernel(const DwPa
   // query stream in while the rows are layer-normed (the launch moves 46 MB of context at 1024
   // points: it is bandwidth bound once the loads overlap).
   const bool has_ctx2 = CAUSAL && p.ctx2_in != nullptr && t0 == 0;
-  float4 ctx_all[SMALL ? kDwSmallQueries : 1][2];
+  // rolling window: the context of queries q .. q + 3 is in flight / in registers; slot q % 4 is
+  // refilled with query q + 4 as soon as query q has consumed it
+  float4 ctx_all[SMALL ? kDwCtxWindow : 1][2];
+  auto fetch_ctx2 = [&](int q, float4 (&dst)[2]) {
+    dst[0] = dst[1] = make_float4(0, 0, 0, 0);
+    if (has_ctx2 && q < nq) {
+      const float* src = p.ctx2_in + ((long long)(n0 + q) * 2) * 2048 + 4 * c;
+      dst[0] = *reinterpret_cast<const float4*>(src);
+      dst[1] = *reinterpret_cast<const float4*>(src + 2048);
+    }
+  };
   if (SMALL) {
 #pragma unroll
-    for (int q = 0; q < kDwSmallQueries; ++q) {
-      ctx_all[q][0] = ctx_all[q][1] = make_float4(0, 0, 0, 0);
-      if (has_ctx2 && q < nq) {
-        const float* src = p.ctx2_in + ((long long)(n0 + q) * 2) * 2048 + 4 * c;
-        ctx_all[q][0] = *reinterpret_cast<const float4*>(src);
-        ctx_all[q][1] = *reinterpret_cast<const float4*>(src + 2048);
-      }
-    }
+    for (int q = 0; q < kDwCtxWindow; ++q) fetch_ctx2(q, ctx_all[q]);
   }
 
   // ---- phase 1: y = LN(x) * w for every needed row (one warp per row)
@@ -464,8 +468,13 @@ __global__ void __launch_bounds__(512, SMALL ? 1 : 2) mixer_dw_kernel(const DwPa
   if constexpr (SMALL) {
     // unrolled so that each copy indexes ctx_all with a constant (it must stay in registers)
 #pragma unroll
-    for (int q = 0; q < kDwSmallQueries; ++q)
-      if (q < nq) per_query(q, ctx_all[q]);
+    for (int q = 0; q < kDwSmallQueries; ++q) {
+      if (q < nq) {
+        const float4 cur[2] = {ctx_all[q % kDwCtxWindow][0], ctx_all[q % kDwCtxWindow][1]};
+        if (q + kDwCtxWindow < kDwSmallQueries) fetch_ctx2(q + kDwCtxWindow, ctx_all[q % kDwCtxWindow]);
+        per_query(q, cur);
+      }
+    }
   } else {
     for (int q = 0; q < nq; ++q) per_query(q, ctx_all[0]);
   }
@@ -669,8 +678,11 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     if (d.QB < 1) d.QB = 1;
     if (d.QB > kDwSmallQueries) d.QB = kDwSmallQueries;
     // few rows in total (streaming): fewer queries per CTA so that every SM gets one
-    // (the several-queries-per-CTA variant runs one CTA per SM)
-    while (d.QB > 2 && (long long)ceil_div(n, d.QB) * ceil_div(T, d.TT) < (long long)num_sms()) d.QB /= 2;
+    // (the several-queries-per-CTA variant runs one CTA per SM: aim at exactly one round)
+    if (d.QB > 1) {
+      const long long per_sm = ceil_div_ll((long long)n * ceil_div(T, d.TT), num_sms());
+      if (per_sm < d.QB) d.QB = per_sm < 2 ? 2 : (int)per_sm;
+    }
     if (d.QB > n) d.QB = n;
     d.ln_w = blk.ln_w; d.w1 = blk.dw1_w; d.b1 = blk.dw1_b; d.w2 = blk.dw2_w; d.b2 = blk.dw2_b;
     d.ln1_w = blk.ln1_w;
