@@ -9,9 +9,9 @@ echo "bench rc=$?"
 python - <<'P'
 import json
 d=json.load(open('gpurun_out/bench_d.json'))
-print('c2', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'e2e8', d['e2e_uint8_frames']['ms_per_step'], d['clocks'])
+print('c2', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'e2e_float', (d.get('e2e_float_frames') or {}).get('ms_per_step'), d['clocks'])
 for k,r in (d.get('sub_records') or {}).items():
-  print(k, r.get('ms_per_step', r.get('ms_per_frame')), (r.get('e2e') or r.get('e2e_uint8_frames') or {}).get('ms_per_step', (r.get('e2e') or {}).get('ms_per_frame')))
+  print(k, r.get('ms_per_step', r.get('ms_per_frame')), (r.get('e2e') or {}).get('ms_per_step', (r.get('e2e') or {}).get('ms_per_frame')))
 kb=d['kernel_breakdown']
 print({k:v['ms_per_step'] for k,v in kb.items() if v['ms_per_step']>0.03})
 print(d['roofline_named']['cost_volume']['issued_mma_frac_of_sustained_peak'], d['roofline_named']['cost_volume']['avg_launch_ms'])

@@ -9,7 +9,7 @@ echo "bench rc=$?"
 python - <<'P'
 import json
 d=json.load(open('gpurun_out/bench_e.json'))
-print('c2', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'e2e8', d['e2e_uint8_frames']['ms_per_step'], d['clocks'])
+print('c2', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'e2e_float', (d.get('e2e_float_frames') or {}).get('ms_per_step'), d['clocks'])
 for k,r in (d.get('sub_records') or {}).items():
-  print(k, r.get('ms_per_step', r.get('ms_per_frame')), (r.get('e2e') or r.get('e2e_uint8_frames') or {}).get('ms_per_step', (r.get('e2e') or {}).get('ms_per_frame')))
+  print(k, r.get('ms_per_step', r.get('ms_per_frame')), (r.get('e2e') or {}).get('ms_per_step', (r.get('e2e') or {}).get('ms_per_frame')))
 P

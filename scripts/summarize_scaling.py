@@ -40,7 +40,7 @@ for n, d in sorted(recs.items()):
   if not r or 'value' not in r:
     continue
   base = base or r['value']
-  e = (r.get('e2e_uint8_frames') or r.get('e2e') or {}).get('ms_per_step')
+  e = (r.get('e2e') or {}).get('ms_per_step')
   L.append(f"| {n} | {r['value']:.0f} | {r['ms_per_step']} | {r['value'] / base:.2f}x | {e} | {(r.get('clocks') or {}).get('sm_mhz')} |")
 L += ['', '## `c5_hires`: BASELINE config 5 (1024x1024x64, 8192 queries in total, three refinement levels)', '',
       '| GPUs | point-frames/s | ms per step | speed-up vs 1 GPU | SM MHz |', '|---|---|---|---|---|']

@@ -113,14 +113,15 @@ constexpr int kStatPixelsPerBlock = 1024;
 
 __global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __restrict__ x,
                                                              long long hw, int C,
-                                                             double* __restrict__ sums) {
+                                                             double* __restrict__ sums,
+                                                             int pixels_per_block) {
   __shared__ double red[256 * 8];
   const int f = blockIdx.y;
   const int c4n = C / 4;             // float4 groups per pixel
   const int lanes = 256 / c4n;       // pixel lanes per block
   const int g = threadIdx.x % c4n, pl = threadIdx.x / c4n;
-  const long long p0 = (long long)blockIdx.x * kStatPixelsPerBlock;
-  long long p1 = p0 + kStatPixelsPerBlock;
+  const long long p0 = (long long)blockIdx.x * pixels_per_block;
+  long long p1 = p0 + pixels_per_block;
   if (p1 > hw) p1 = hw;
   double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
   if (pl < lanes) {
@@ -401,9 +402,11 @@ int instnorm_stats(const float* x, int frames, long long hw, int C, double* sums
   TAPIR_CHECK_ARG(C == 64 || C == 128 || C == 256, "instnorm_stats: C=%d unsupported", C);
   ProfileScope ps("backbone.instnorm_stats", s, 0.0, (double)frames * hw * C * 4);
   TAPIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * frames * C, s));
-  // single frames (streaming): keep every SM busy
-  dim3 grid((unsigned)ceil_div_ll(hw, kStatPixelsPerBlock), frames);
-  instnorm_stats_kernel<<<grid, 256, 0, s>>>(x, hw, C, sums);
+  // single frames (streaming): 1024-pixel blocks would be 16 CTAs; shrink until every SM has one
+  int ppb = kStatPixelsPerBlock;
+  while (ppb > 64 && ceil_div_ll(hw, ppb) * frames < (long long)num_sms()) ppb /= 2;
+  dim3 grid((unsigned)ceil_div_ll(hw, ppb), frames);
+  instnorm_stats_kernel<<<grid, 256, 0, s>>>(x, hw, C, sums, ppb);
   count_launch();
   TAPIR_LAUNCH_CHECK("instnorm_stats_kernel");
   return kOk;
