@@ -674,7 +674,7 @@ int backbone_forward(const tapir_backbone_weights* w, const void* video, int vid
     {
       GemmArgs g = linear_args(b.conv);
       g.tag = "backbone.extra_conv";
-      g.splitk_ws = bp.splitk; g.splitk_ws_bytes = kBackboneSplitKBytes;
+      g.splitk_ws = bp.splitk; g.splitk_ws_bytes = kBackboneSplitKBytes; g.allow_splitk = (frames == 1);
       g.mode = kGemmConv3x3;
       g.M = (int)m;
       g.a = bp.act; g.a_plane_stride = bp.act_plane;
@@ -686,7 +686,7 @@ int backbone_forward(const tapir_backbone_weights* w, const void* video, int vid
     {
       GemmArgs g = linear_args(b.conv1);
       g.tag = "backbone.extra_conv";
-      g.splitk_ws = bp.splitk; g.splitk_ws_bytes = kBackboneSplitKBytes;
+      g.splitk_ws = bp.splitk; g.splitk_ws_bytes = kBackboneSplitKBytes; g.allow_splitk = (frames == 1);
       g.mode = kGemmConv3x3;
       g.M = (int)m;
       g.a = bp.col; g.a_plane_stride = bp.col_plane;

@@ -46,6 +46,10 @@ struct GemmArgs {
   int rows_per_frame = 0;   // plain mode: rows per frame (multiple of 128); conv: implied
   float* splitk_ws = nullptr;  // optional scratch enabling split-K for under-filled problems
   size_t splitk_ws_bytes = 0;
+  // Callers set this for single-frame (streaming) steps only: a split GEMM sums K in a different
+  // order, so allowing it by problem size alone would make an offline result depend on how its
+  // rows were chunked or sharded (measured: 1.5e-5 on occlusion logits).
+  bool allow_splitk = false;
   int k_logical = 0;        // un-padded K for FLOP accounting (0 = K)
   const char* tag = nullptr;  // profiling class name
 };

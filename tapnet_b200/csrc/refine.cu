@@ -659,7 +659,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
   {  // nets.py:235 linear
     GemmArgs g = lin(w->linear);
     g.tag = "mixer.linear_in";
-    g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes;
+    g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes; g.allow_splitk = (T == 1);
     g.M = (int)rows;
     g.a = static_cast<const __nv_bfloat16*>(io->x_planes);
     g.lda = io->ldx;
@@ -708,7 +708,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     {
       GemmArgs g = lin(blk.up);
       g.tag = "mixer.up";
-      g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes;
+      g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes; g.allow_splitk = (T == 1);
       g.M = (int)rows;
       g.a = m.y; g.lda = 512; g.a_plane_stride = rows * 512;
       g.act = 1;
@@ -718,7 +718,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
     {
       GemmArgs g = lin(blk.down);
       g.tag = "mixer.down";
-      g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes;
+      g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes; g.allow_splitk = (T == 1);
       g.M = (int)rows;
       g.a = m.h; g.lda = 2048; g.a_plane_stride = rows * 2048;
       g.residual = m.xb; g.ldr = 512;
@@ -730,7 +730,7 @@ int mixer_forward(const tapir_mixer_weights* w, const tapir_mixer_io* io, void* 
   {
     GemmArgs g = lin(w->linear_1);
     g.tag = "mixer.linear_out";
-    g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes;
+    g.splitk_ws = m.splitk; g.splitk_ws_bytes = kSplitKBytes; g.allow_splitk = (T == 1);
     g.M = (int)rows;
     g.a = m.y; g.lda = 512; g.a_plane_stride = rows * 512;
     g.out_f32 = io->out; g.ldo = io->ldo;
