@@ -40,9 +40,6 @@ def choice(m_rows, n, planes, tail=True):
   m_tiles = math.ceil(m_rows / 128)
   pr = (m_tiles + 1) // 2
   small = 2 * pr * math.ceil(n / 128) * 10 < SMS * 6
-  if n == 64 and m_tiles >= 2 and not small:  # first ResNet group: 256 x 64 pair tiles
-    tiles = pr
-    return '2SM 256x64', tiles, SMS // 2, math.ceil(tiles / (SMS // 2))
   if n >= 128 and m_tiles >= 2 and not small:
     c128, _ = _tail_plan(pr, n, 128, tail)
     c256, _ = _tail_plan(pr, n, 256, tail)

@@ -72,10 +72,6 @@ struct TcParams {
   // chunks) so that the partial last round spreads over all clusters instead of a few.
   CUtensorMap tmB16;    // B with a 16-row box: pieces load their half-width in 16-row slabs
   int tail_first, tail_k, tail_base, tail_extra;
-  // 2-SM kernel, weight-stationary mode (one tile column, e.g. the N = 64 ResNet layers): every
-  // CTA loads its half of the WHOLE weight matrix once and keeps it in shared memory; the ring then
-  // carries A only (`res_stages` stages of P x 16 KB).
-  int b_resident, res_stages;
 };
 
 template <int BLOCK_N, int P>
@@ -484,7 +480,7 @@ struct Tc2Cfg {
   static constexpr int kBhBytes = (BN / 2) * kBlockK * 2;
   static constexpr int kStageBytes = P * (kABytes + kBhBytes);
   static constexpr int kEpiWarps = 16;
-  static constexpr int kChunks = BN >= 128 ? BN / 32 / 4 : 1;  // 32-column chunks per epilogue warp
+  static constexpr int kChunks = BN / 32 / 4;
   static constexpr int kBiasBytes = kEpiWarps * kChunks * 32 * 4;
   static constexpr int kAvail = kSmemLimit - 1024 - kBarrierBytes - kBiasBytes;
   static constexpr int kStagesRaw = kAvail / kStageBytes;
@@ -493,7 +489,7 @@ struct Tc2Cfg {
   static constexpr int kTmemCols = kNumAccStages * BN;  // 256 or 512
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static_assert(kStages >= 2, "tile does not fit in shared memory");
-  static_assert(BN == 64 || BN == 128 || BN == 256, "pair tile width");
+  static_assert(BN == 128 || BN == 256, "pair tile width");
 };
 
 template <int BN, int P>
@@ -509,13 +505,7 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + kNumAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kNumAccStages);
-  uint64_t* bres_bar = tmem_empty_bar + kNumAccStages + 1;  // resident-B arrival (leader's)
   float* bias_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + kBarrierBytes);
-  // weight-stationary mode: A-only ring in front, the resident B half behind it
-  const bool bres = p.b_resident != 0;
-  const int num_stages = bres ? p.res_stages : Cfg::kStages;
-  const int stage_bytes = bres ? P * Cfg::kABytes : Cfg::kStageBytes;
-  uint8_t* b_res = smem + num_stages * stage_bytes;  // [k-block][plane][BN/2 rows][128 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -533,7 +523,6 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       ptx::mbar_init(&tmem_full_bar[a], 1);                    // pair commit, multicast
       ptx::mbar_init(&tmem_empty_bar[a], 2 * Cfg::kEpiWarps);  // epilogue warps of BOTH CTAs
     }
-    ptx::mbar_init(bres_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&p.tmA);
     ptx::prefetch_tensormap(&p.tmBh);
@@ -577,14 +566,6 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
     // ------------------------------------------------------------------ TMA producer (each CTA)
     int stage = 0;
     uint32_t phase = 0;
-    if (bres && work_first < num_work) {  // the whole weight matrix (this CTA's half of the rows), once
-      if (leader) ptx::mbar_arrive_expect_tx(bres_bar, 2u * (uint32_t)nkb * P * Cfg::kBhBytes);
-      for (int kb = 0; kb < nkb; ++kb)
-#pragma unroll
-        for (int pl = 0; pl < P; ++pl)
-          ptx::tma_load_3d_2sm(b_res + (kb * P + pl) * Cfg::kBhBytes, &p.tmBh, bres_bar, kb * kBlockK,
-                               rank * (BN / 2), pl);
-    }
     for (int w = work_first; w < num_work; w += work_stride) {
       int m_tile, n0, width;
       decode(w, m_tile, n0, width);
@@ -598,11 +579,11 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
         x0 = (r % p.tiles_x) * p.tileW;
       }
       const int half = width / 2;  // B rows this CTA loads (each row = one 128-byte swizzle row)
-      const uint32_t stage_tx = 2u * P * (uint32_t)(Cfg::kABytes + (bres ? 0 : half * kBlockK * 2));
+      const uint32_t stage_tx = 2u * P * (uint32_t)(Cfg::kABytes + half * kBlockK * 2);
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 201);
         if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + P * Cfg::kABytes;
         if (p.mode == kGemmConv3x3) {
           const int tap = kb / p.cblocks;
@@ -618,9 +599,7 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
             ptx::tma_load_3d_2sm(sa + pl * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * kBlockK,
                                  m_tile * kBlockM, pl);
         }
-        if (bres) {
-          // weights are resident
-        } else if (width == BN) {
+        if (width == BN) {
 #pragma unroll
           for (int pl = 0; pl < P; ++pl)
             ptx::tma_load_3d_2sm(sb + pl * Cfg::kBhBytes, &p.tmBh, &full_bar[stage], kb * kBlockK,
@@ -632,7 +611,7 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
               ptx::tma_load_3d_2sm(sb + pl * Cfg::kBhBytes + r16 * (kBlockK * 2), &p.tmB16, &full_bar[stage],
                                    kb * kBlockK, n0 + rank * half + r16, pl);
         }
-        if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == kMmaWarp && lane == 0 && leader) {
@@ -640,10 +619,6 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    if (bres && work_first < num_work) {
-      ptx::mbar_wait(bres_bar, 0u, p.err, 205);
-      ptx::tc_fence_after();
-    }
     for (int w = work_first; w < num_work; w += work_stride) {
       int m_tile_unused, n0_unused, width;
       decode(w, m_tile_unused, n0_unused, width);
@@ -658,8 +633,8 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
       for (int kb = 0; kb < nkb; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase, p.err, 203);
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
-        const uint32_t sb = bres ? ptx::smem_u32(b_res + kb * P * Cfg::kBhBytes) : sa + P * Cfg::kABytes;
+        const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + P * Cfg::kABytes;
         uint32_t accumulate = (kb > 0) ? 1u : 0u;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
@@ -675,7 +650,7 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
           }
         }
         ptx::umma_commit_2sm(&empty_bar[stage]);  // both producers may refill the slot
-        if (++stage == num_stages) { stage = 0; phase ^= 1u; }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
       ptx::umma_commit_2sm(&tmem_full_bar[acc]);  // both epilogues may read their TMEM half
     }
@@ -1087,13 +1062,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
   }
 
   // 2-SM path (cta_group::2): pair tiles of 256 x {128, 256}
-  // (N = 64 layers - the first ResNet group - included: 256 x 64 pair tiles share each weight
-  // tile between two SMs, and these layers are bound by L2 -> SM operand traffic, DESIGN.md 9.2;
-  // TAPIR_B200_GEMM_2SM_N64=1 enables it)
-  static int n64_on = -1;
-  if (n64_on < 0) { const char* e = getenv("TAPIR_B200_GEMM_2SM_N64"); n64_on = (e != nullptr && atoi(e) != 0) ? 1 : 0; }  // opt-in until validated on a GPU
-  const bool wide_enough = g.N >= 128 || (n64_on && g.N == 64);
-  if (use_2sm() != 0 && wide_enough && p.num_m_tiles >= 2 && (num_sms() % 2 == 0) &&
+  if (use_2sm() != 0 && g.N >= 128 && p.num_m_tiles >= 2 && (num_sms() % 2 == 0) &&
       !small_problem(p.num_m_tiles, g.N)) {
     int bn2 = use_2sm();
     static int tail_on = -1;
@@ -1130,13 +1099,10 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
       const long long c256 = tail_plan(256, &tf, &tk, &tb, &te);
       // three planes (the cost volume: 6 MMAs per k-block, only two 96 KB stages fit at 256 columns,
       // few tiles per CTA so fill / drain matter): no bias towards the wide tile
-      static int bias_env = -1;  // bring-up A/B of the tile-width policy (TAPIR_B200_GEMM_BIAS=9|10)
-      if (bias_env < 0) { const char* e = getenv("TAPIR_B200_GEMM_BIAS"); bias_env = e != nullptr ? atoi(e) : 0; }
-      const long long bias = bias_env > 0 ? bias_env : ((P == 3) ? 10 : 9);
+      const long long bias = (P == 3) ? 10 : 9;
       bn2 = (g.N >= 256 && c256 * bias <= c128 * 10) ? 256 : 128;
     }
     if (bn2 == 256 && g.N < 256) bn2 = 128;
-    if (g.N == 64) bn2 = 64;
     const long long plane = g.b_plane_stride > 0 ? g.b_plane_stride : (long long)g.N * g.ldb;
     cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.N, (cuuint64_t)P};
     cuuint64_t str[2] = {(cuuint64_t)g.ldb * 2, (cuuint64_t)plane * 2};
@@ -1151,33 +1117,6 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     // rows: 384 tiles on 74 clusters = 5 rounds + 14 tiles).  Those tiles are cut along N into k
     // pieces of 32-column chunks with k * (W % C) <= C, so the last round costs about 1/k-th.
     tail_plan(bn2, &p.tail_first, &p.tail_k, &p.tail_base, &p.tail_extra);
-    {
-      // weight-stationary mode (opt-in, TAPIR_B200_GEMM_BRES=1): one tile column and the CTA's half
-      // of the weights leaves room for at least 3 A-only stages
-      static int bres_on = -1;
-      if (bres_on < 0) { const char* e = getenv("TAPIR_B200_GEMM_BRES"); bres_on = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
-      p.b_resident = 0;
-      p.res_stages = 0;
-      if (bres_on && ceil_div(g.N, bn2) == 1 && bn2 <= 128 && p.tail_k == 1) {  // (pieces need other B rows)
-        const long long a_stage = (long long)P * kBlockM * kBlockK * 2;
-        const long long bh = (long long)p.num_k_blocks * P * (bn2 / 2) * kBlockK * 2;
-        long long total = 0;
-        if (bn2 == 64) total = (P == 1 ? Tc2Cfg<64, 1>::kStages * (long long)Tc2Cfg<64, 1>::kStageBytes
-                               : P == 2 ? Tc2Cfg<64, 2>::kStages * (long long)Tc2Cfg<64, 2>::kStageBytes
-                                        : Tc2Cfg<64, 3>::kStages * (long long)Tc2Cfg<64, 3>::kStageBytes);
-        else total = (P == 1 ? Tc2Cfg<128, 1>::kStages * (long long)Tc2Cfg<128, 1>::kStageBytes
-                     : P == 2 ? Tc2Cfg<128, 2>::kStages * (long long)Tc2Cfg<128, 2>::kStageBytes
-                              : Tc2Cfg<128, 3>::kStages * (long long)Tc2Cfg<128, 3>::kStageBytes);
-        long long st = (total - bh) / a_stage;
-        const int max_st = bn2 == 64 ? (P == 1 ? Tc2Cfg<64, 1>::kStages : P == 2 ? Tc2Cfg<64, 2>::kStages : Tc2Cfg<64, 3>::kStages)
-                                     : (P == 1 ? Tc2Cfg<128, 1>::kStages : P == 2 ? Tc2Cfg<128, 2>::kStages : Tc2Cfg<128, 3>::kStages);
-        if (st > max_st) st = max_st;
-        if (bh < total && st >= 3) { p.b_resident = 1; p.res_stages = (int)st; }
-      }
-    }
-    if (bn2 == 64 && P == 1) return launch2<64, 1>(p, g, stream);
-    if (bn2 == 64 && P == 2) return launch2<64, 2>(p, g, stream);
-    if (bn2 == 64 && P == 3) return launch2<64, 3>(p, g, stream);
     if (bn2 == 128 && P == 1) return launch2<128, 1>(p, g, stream);
     if (bn2 == 128 && P == 2) return launch2<128, 2>(p, g, stream);
     if (bn2 == 256 && P == 1) return launch2<256, 1>(p, g, stream);
