@@ -72,6 +72,7 @@ struct TcParams {
   // chunks) so that the partial last round spreads over all clusters instead of a few.
   CUtensorMap tmB16;    // B with a 16-row box: pieces load their half-width in 16-row slabs
   int tail_first, tail_k, tail_base, tail_extra;
+  CUtensorMap tmPatch;  // halo convolution: one patch row {64 ch, 10 px} per load
 };
 
 template <int BLOCK_N, int P>
@@ -729,6 +730,181 @@ gemm_tc2_kernel(const __grid_constant__ TcParams p) {
 }
 
 
+// ------------------------------------------------------------------------------ halo-patch conv
+// 3x3 convolution, C = 64 -> N = 64 (the first ResNet group, stride 1).  The generic implicit GEMM
+// loads one shifted 128-pixel box per tap: every input element crosses L2 -> SM nine times and
+// these layers ran at the L2 limit (2.7 GB per launch, 300 us against a 109 us MMA bound).  Here a
+// tile of 8 x 16 output pixels stages its 10 x 18 input patch ONCE (18 TMA loads of one patch row
+// each into rows padded to 16 pixels = 2048 B, so that every 8-pixel group of every tap view has the
+// same swizzle phase) and the nine taps are nine shared-memory views of it: start = patch +
+// ky * 2048 + kx * 128, 2048 B between row groups (ptx::make_smem_desc_sw128_view).
+// B (weights, 8 KB per tap and plane) streams through a 4-slot ring.  Epilogue as in gemm_tc_kernel.
+constexpr int kHaloTileW = 8, kHaloTileH = 16;
+constexpr int kHaloRowBytes = 2048;                        // 16 pixels x 128 B
+constexpr int kHaloPatchRows = kHaloTileH + 2;
+constexpr int kHaloPatchBytes = kHaloPatchRows * kHaloRowBytes;  // per plane
+constexpr int kHaloRowLoadBytes = (kHaloTileW + 2) * 128;  // what one TMA row load delivers
+constexpr int kHaloBStages = 4;
+constexpr int kHaloBBytes = 64 * 128;                      // per plane and tap
+template <int P>
+struct HaloCfg {
+  static constexpr int kPatchStage = P * kHaloPatchBytes;
+  static constexpr int kBStage = P * kHaloBBytes;
+  static constexpr int kEpiWarps = epi_warps(64);
+  static constexpr int kBiasBytes = kEpiWarps * 32 * 4;
+  static constexpr int kSmemBytes = 1024 + 2 * kPatchStage + kHaloBStages * kBStage + kBarrierBytes + kBiasBytes;
+  static constexpr int kThreads = num_threads(64);
+  static_assert(kSmemBytes <= kSmemLimit, "halo conv: shared memory");
+};
+
+template <int P>
+__global__ void __launch_bounds__(HaloCfg<P>::kThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ TcParams p) {
+  using Cfg = HaloCfg<P>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* patch = smem;                                   // [2][P][18][2048]
+  uint8_t* bring = smem + 2 * Cfg::kPatchStage;            // [4][P][64][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bring + kHaloBStages * Cfg::kBStage);
+  uint64_t* pfull = bars;                    // [2]
+  uint64_t* pempty = bars + 2;               // [2]
+  uint64_t* bfull = bars + 4;                // [4]
+  uint64_t* bempty = bars + 8;               // [4]
+  uint64_t* tmem_full_bar = bars + 12;       // [2]
+  uint64_t* tmem_empty_bar = bars + 14;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* bias_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarrierBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr int kProducerWarp = Cfg::kEpiWarps;
+  constexpr int kMmaWarp = Cfg::kEpiWarps + 1;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&pfull[s], 1); ptx::mbar_init(&pempty[s], 1); }
+    for (int s = 0; s < kHaloBStages; ++s) { ptx::mbar_init(&bfull[s], 1); ptx::mbar_init(&bempty[s], 1); }
+    for (int a = 0; a < kNumAccStages; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], Cfg::kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&p.tmPatch);
+    ptx::prefetch_tensormap(&p.tmB);
+  }
+  if (warp == kMmaWarp) {
+    ptx::tmem_alloc(tmem_slot, 128);  // two 64-column accumulators
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_work = p.num_m_tiles;
+  const int per_frame = p.tiles_x * p.tiles_y;
+
+  if (warp == kProducerWarp && lane == 0) {
+    int ps = 0, bs = 0;
+    uint32_t pphase = 0, bphase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int frame = w / per_frame;
+      const int r = w - frame * per_frame;
+      const int y0 = (r / p.tiles_x) * kHaloTileH, x0 = (r % p.tiles_x) * kHaloTileW;
+      ptx::mbar_wait(&pempty[ps], pphase ^ 1u, p.err, 401);
+      ptx::mbar_arrive_expect_tx(&pfull[ps], (uint32_t)(P * kHaloPatchRows * kHaloRowLoadBytes));
+      for (int pl = 0; pl < P; ++pl)
+        for (int pr = 0; pr < kHaloPatchRows; ++pr)
+          ptx::tma_load_5d(patch + ps * Cfg::kPatchStage + pl * kHaloPatchBytes + pr * kHaloRowBytes, &p.tmPatch,
+                           &pfull[ps], 0, x0 - 1, y0 - 1 + pr, frame, pl);
+      if (++ps == 2) { ps = 0; pphase ^= 1u; }
+      for (int tap = 0; tap < 9; ++tap) {
+        ptx::mbar_wait(&bempty[bs], bphase ^ 1u, p.err, 402);
+        ptx::mbar_arrive_expect_tx(&bfull[bs], (uint32_t)Cfg::kBStage);
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl)
+          ptx::tma_load_3d(bring + bs * Cfg::kBStage + pl * kHaloBBytes, &p.tmB, &bfull[bs], tap * kBlockK, 0, pl);
+        if (++bs == kHaloBStages) { bs = 0; bphase ^= 1u; }
+      }
+    }
+  } else if (warp == kMmaWarp && lane == 0) {
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, 64);
+    int ps = 0, bs = 0, it = 0;
+    uint32_t pphase = 0, bphase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, p.err, 403);
+      ptx::mbar_wait(&pfull[ps], pphase, p.err, 404);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 64;
+      const uint32_t pbase = ptx::smem_u32(patch + ps * Cfg::kPatchStage);
+      uint32_t accumulate = 0u;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - ky * 3;
+        ptx::mbar_wait(&bfull[bs], bphase, p.err, 405);
+        ptx::tc_fence_after();
+        const uint32_t sb = ptx::smem_u32(bring + bs * Cfg::kBStage);
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+#pragma unroll
+          for (int j = 0; j < P - i; ++j) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128_view(
+                pbase + i * kHaloPatchBytes + ky * kHaloRowBytes + kx * 128, kHaloRowBytes);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + j * kHaloBBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              ptx::umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+              accumulate = 1u;
+            }
+          }
+        }
+        ptx::umma_commit(&bempty[bs]);
+        if (++bs == kHaloBStages) { bs = 0; bphase ^= 1u; }
+      }
+      ptx::umma_commit(&pempty[ps]);
+      ptx::umma_commit(&tmem_full_bar[acc]);
+      if (++ps == 2) { ps = 0; pphase ^= 1u; }
+    }
+  } else if (warp < Cfg::kEpiWarps) {
+    const int q = warp & 3;
+    const int chunk = warp >> 2;  // 2 column groups x one 32-column chunk
+    float* bias_w = bias_smem + warp * 32;
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int frame = w / per_frame;
+      const int rr = w - frame * per_frame;
+      const int r = q * 32 + lane;
+      const int y = (rr / p.tiles_x) * kHaloTileH + r / kHaloTileW;
+      const int x = (rr % p.tiles_x) * kHaloTileW + r % kHaloTileW;
+      const bool row_ok = (y < p.H) && (x < p.W);
+      const long long row = ((long long)frame * p.H + y) * p.W + x;
+      const int col0 = chunk * 32;
+      if (p.bias != nullptr) {
+        __syncwarp();
+        bias_w[lane] = (col0 + lane < p.N) ? __ldg(p.bias + col0 + lane) : 0.f;
+        __syncwarp();
+      }
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase, p.err, 406);
+      ptx::tc_fence_after();
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 64 + col0, v);
+      ptx::tmem_ld_wait();
+      if (row_ok || p.stats != nullptr) store_row_chunk(p, row, col0, v, bias_w, row_ok, frame, lane, 0);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 128);
+  }
+}
+
+
 // Second pass of a split-K GEMM: sums the k-slice partials in a fixed order (deterministic) and
 // applies the epilogue (bias, GELU, residual, fp32 / bf16-plane outputs).
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int S,
@@ -1032,6 +1208,47 @@ int gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     cuuint64_t str[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)plane * 2};
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)kBlockM, 1};
     TAPIR_RETURN_IF(encode_bf16_map(&p.tmA, g.a, 3, dims, str, box, "A"));
+  }
+  // Halo-patch kernel for the C = 64 -> 64 3x3 layers (first ResNet group), see conv3x3_halo_kernel.
+  {
+    static int halo_on = -1;
+    if (halo_on < 0) { const char* e = getenv("TAPIR_B200_CONV_HALO"); halo_on = (e != nullptr && atoi(e) == 0) ? 0 : 1; }  // TAPIR_B200_CONV_HALO=0: generic path
+    if (halo_on && g.mode == kGemmConv3x3 && g.C == 64 && g.N == 64 && P <= 2 && g.out_planes == nullptr) {
+      p.tileW = kHaloTileW;
+      p.tileH = kHaloTileH;
+      p.tiles_x = ceil_div(g.W, kHaloTileW);
+      p.tiles_y = ceil_div(g.H, kHaloTileH);
+      p.num_m_tiles = g.frames * p.tiles_x * p.tiles_y;
+      p.num_n_tiles = 1;
+      p.split_k = 1;
+      const long long aplane = g.a_plane_stride > 0 ? g.a_plane_stride : (long long)g.M * g.C;
+      cuuint64_t adims[5] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.frames, (cuuint64_t)P};
+      cuuint64_t astr[4] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2,
+                            (cuuint64_t)aplane * 2};
+      cuuint32_t abox[5] = {(cuuint32_t)kBlockK, (cuuint32_t)(kHaloTileW + 2), 1, 1, 1};
+      TAPIR_RETURN_IF(encode_bf16_map(&p.tmPatch, g.a, 5, adims, astr, abox, "A/patch"));
+      const long long bplane = g.b_plane_stride > 0 ? g.b_plane_stride : (long long)g.N * g.ldb;
+      cuuint64_t bdims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.N, (cuuint64_t)P};
+      cuuint64_t bstr[2] = {(cuuint64_t)g.ldb * 2, (cuuint64_t)bplane * 2};
+      cuuint32_t bbox[3] = {(cuuint32_t)kBlockK, 64, 1};
+      TAPIR_RETURN_IF(encode_bf16_map(&p.tmB, g.b, 3, bdims, bstr, bbox, "B/halo"));
+      static PerDeviceOnce configured;
+      if (configured.pending()) {
+        TAPIR_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<1>::kSmemBytes));
+        TAPIR_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<2>::kSmemBytes));
+        configured.mark();
+      }
+      const double kl = g.k_logical > 0 ? g.k_logical : g.K;
+      const double out_b = (g.out_f32 ? 4.0 : 0.0) + (g.residual ? 4.0 : 0.0);
+      ProfileScope ps(g.tag ? g.tag : "gemm", stream, 2.0 * g.M * g.N * kl,
+                      2.0 * P * ((double)g.M * g.C + (double)g.N * g.K) + out_b * g.M * g.N);
+      const int grid = p.num_m_tiles < num_sms() ? p.num_m_tiles : num_sms();
+      if (P == 1) conv3x3_halo_kernel<1><<<grid, HaloCfg<1>::kThreads, HaloCfg<1>::kSmemBytes, stream>>>(p);
+      else conv3x3_halo_kernel<2><<<grid, HaloCfg<2>::kThreads, HaloCfg<2>::kSmemBytes, stream>>>(p);
+      count_launch();
+      TAPIR_LAUNCH_CHECK("conv3x3_halo_kernel");
+      return kOk;
+    }
   }
   // Split-K (deterministic two-pass, below) for problems that cannot half-fill the GPU: on by
   // default, TAPIR_B200_SPLITK=0 disables.  (Round 1 measured "no gain at K = 2048" with a launch

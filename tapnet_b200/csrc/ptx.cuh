@@ -259,6 +259,22 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
   return d;
 }
 
+// Same, for a VIEW into a staged tile that does not start on a swizzle-atom boundary: the groups
+// of eight rows are `sbo_bytes` apart (they need not be contiguous) and the first row may sit any
+// number of 128-byte rows into its 1024-byte swizzle pattern.  Measured on B200 (round 2, the
+// halo-patch convolution): the tensor core applies the 128B swizzle from the ABSOLUTE shared-memory
+// address bits, exactly as TMA does when it writes the tile, so such a view needs NO base offset
+// (descriptor bits 49-51 stay 0; declaring the row phase there gives wrong data).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_view(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+
 // Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1),
 // both K-major (bits 15,16 = 0), N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
