@@ -127,3 +127,36 @@ def test_fused_instance_norm_statistics(mode, impl):
   err = ((stats - ref).abs() / ref.abs().clamp(min=1.0)).max().item()
   U.record(f'gemm_stats_{mode}_impl{impl}', rel_err=err)
   assert err < 5e-5
+
+
+def test_halo_conv_is_bit_identical_to_the_generic_implicit_gemm():
+  """conv3x3_halo_kernel (C = 64 -> 64) accumulates every output element in the same order as the
+  generic implicit GEMM: same bits.  The switch is read once per process, so each variant runs in
+  its own interpreter and reports a digest of the output."""
+  import hashlib
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  code = (
+      "import hashlib, sys, torch\n"
+      f"sys.path.insert(0, {root!r})\n"
+      "from tests import gpu_util as U\n"
+      "g = torch.Generator().manual_seed(3)\n"
+      "Fr, H, W, C = 3, 40, 56, 64\n"
+      "x = torch.randn(Fr, H, W, C, generator=g).cuda()\n"
+      "w = (torch.randn(64, 9 * C, generator=g) / 24).cuda()\n"
+      "b = torch.randn(64, generator=g).cuda()\n"
+      "r = torch.randn(Fr * H * W, 64, generator=g).cuda()\n"
+      "st = torch.zeros(Fr, 64, 2, dtype=torch.float64, device='cuda')\n"
+      "xp = U.split(x.reshape(-1, C), 2).reshape(2, Fr, H, W, C)\n"
+      "o, _ = U.gemm(xp, U.split(w, 2), b, r, False, True, 0, 0, conv=(Fr, H, W, C), stats=st)\n"
+      "print('DIGEST', hashlib.sha256(o.cpu().numpy().tobytes()).hexdigest(), float(o.abs().sum()))\n")
+  digests = []
+  for halo in ('1', '0'):
+    env = dict(os.environ, TAPIR_B200_CONV_HALO=halo)
+    p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    digests.append([l for l in p.stdout.splitlines() if l.startswith('DIGEST')][0])
+  U.record('halo_vs_generic', identical=int(digests[0] == digests[1]))
+  assert digests[0] == digests[1], digests
