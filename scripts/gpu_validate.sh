@@ -1,4 +1,6 @@
 #!/bin/bash
+# Full GPU validation pass: the whole -m gpu suite, then the default bench line (headline + sub-records).
+# Usage: gpurun -- bash scripts/gpu_validate.sh
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -q -m gpu --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
