@@ -396,7 +396,6 @@ def run_c3_stream(R):
     return e0.elapsed_time(e1) / F, R.sampler.window(t0, t1)
 
   trk = streaming.OnlineTracker(cm, res, res, n)
-  launches0 = R.lib.tapir_launch_count()
   trk.init(clip_d[0], q)
   trk.step(clip_d[0])  # captures the graph (launch counter advances while capturing)
   ms_dev, clocks = run(trk, clip_d, False)
@@ -421,7 +420,6 @@ def run_c3_stream(R):
   eager()
   per_frame_launches = int(R.lib.tapir_launch_count() - l0)
   _, breakdown = R.profile(eager, 4)
-  del launches0
   return dict(
       metric='causal online tracking, ms per frame (1 frame per step, causal state carried)',
       config=dict(workload=f"causal BootsTAPIR streaming {res}x{res}, {n} points, {F} frames after "
@@ -501,12 +499,11 @@ def run_ours(args):
           kernel='cost_volume.head', bound='cuda-core / shared memory',
           achieved=round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 2), unit='TFLOP/s',
           avg_launch_ms=round(v['ms'] / max(v['launches'], 1), 4), launches=per_step['cost_volume.head']['launches'])
+  wl = WORKLOADS[args.workload]
   cpu_baseline = None
   if world == 1 and not args.no_cpu:
-    wl = WORKLOADS[args.workload]
     video_h, queries_h = build_inputs(wl, world)
     cpu_baseline = cpu_reference(R.sd, video_h, queries_h, wl, repeats=3)
-  wl = WORKLOADS[args.workload]
   line = dict(
       metric=main['metric'], value=main['value'], unit=UNIT, n_gpus=world, steps=args.steps,
       warmup=max(args.warmup, 3), ms_per_step=main['ms_per_step'], higher_is_better=True,
