@@ -110,3 +110,50 @@ def test_live_crop_window_matches_reference_slicing():
       want = image
     y0, x0, ch, cw = live.center_square_window(h, w)
     np.testing.assert_array_equal(image[y0:y0 + ch, x0:x0 + cw], want)
+
+
+def test_build_model_dispatches_on_haiku_npy(tmp_path):
+  """build_model('x.npy'): the Haiku tree goes through convert.py (bulk.track_many_points
+  is handed such a path); constructor arguments are inferred from the tree."""
+  import numpy as np
+  from tapnet_b200 import convert
+  sd = synth.make_state_dict(3, pyramid_level=0, extra_convs=False)
+  tree = convert.to_haiku_params(sd, pyramid_level=0, extra_convs=False)
+  path = tmp_path / 'ckpt.npy'
+  np.save(path, {'params': tree}, allow_pickle=True)
+  m = tapir_model.build_model(str(path), device='cpu')
+  assert m.pyramid_level == 0 and m.extra_convs is None
+  got = m.state_dict()
+  assert list(got.keys()) == list(sd.keys())
+  for k in sd:
+    assert torch.equal(got[k], sd[k]), k
+
+
+def test_workspace_is_grow_only_and_parked_while_pinned():
+  """TAPIR._workspace: a captured CUDA graph holds raw pointers into these buffers, so
+  an outgrown buffer is parked, not freed, while a tracker pins the model; the generation counter
+  tells graph owners that their capture is stale."""
+  m = tapir_model.TAPIR()
+  cpu = torch.device('cpu')
+  a = m._workspace('mixer', 100, cpu)
+  g0 = m._ws_generation
+  assert m._workspace('mixer', 50, cpu) is a and m._ws_generation == g0   # reuse, no growth
+  m._ws_pins += 1                                                          # a tracker captured
+  b = m._workspace('mixer', 1000, cpu)
+  assert b is not a and m._ws_generation == g0 + 1
+  assert any(t is a for t in m._ws_retired)                                # parked, still alive
+  m._ws_pins -= 1
+  c = m._workspace('mixer', 5000, cpu)
+  assert c is not b and not any(t is b for t in m._ws_retired)             # unpinned: dropped
+
+
+def test_param_signature_notices_in_place_updates_and_reload():
+  m = tapir_model.TAPIR()
+  s0 = m._param_sig()
+  assert m._param_sig() == s0
+  with torch.no_grad():
+    next(m.parameters()).add_(1.0)
+  s1 = m._param_sig()
+  assert s1 != s0
+  m.load_state_dict(synth.make_state_dict(1))
+  assert m._param_sig() != s1
