@@ -25,8 +25,8 @@ CASES = [
     (16, 8192, 256, 3, False, False, False, 0),
     (20000, 512, 576, 2, True, False, False, 0),
     # shapes whose persistent schedule ends in a partial round: the tail tiles are cut along N
-    # (mixer `up`: 5 pieces of 64/64/64/32/32 columns; `down`: 96/96/64; linear_out: 32-column
-    # pieces, an odd number of row tiles and pieces beyond N = 388)
+    # into pieces of at least 64 columns (mixer `up` and `down`; linear_out: an odd number of row
+    # tiles and pieces that reach beyond N = 388)
     (12288, 2048, 512, 2, True, True, False, 2),
     (12288, 512, 2048, 2, True, False, True, 0),
     (9600, 388, 512, 2, True, False, False, 0),
